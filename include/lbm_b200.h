@@ -1,0 +1,145 @@
+/*
+ * lbm_b200.h -- C ABI of liblbm_b200.so, the B200-native D2Q9-BGK lattice-Boltzmann solver.
+ *
+ * This is the drop-in boundary for the hot path of thorbenlouw/lbm-graphcore
+ * (accelerate_flow -> propagate -> rebound -> collision + av_velocity).  The reference has no
+ * FFI layer; its seam is the Poplar `Engine` as driven by main/LbmRunner.cpp (identically by
+ * main/LbmAoS.cpp:402-424): named caller-owned host buffers plus three numbered programs and a
+ * device timer.  Each entry point below names the reference call it replaces.
+ *
+ * Conventions (same as the reference's use of the Engine):
+ *   - plain C types only; no CUDA or torch types cross the boundary;
+ *   - host buffers are OWNED BY THE CALLER and are only read/written during the call;
+ *   - cells are AoS float[ny][nx][9] (main/include/LatticeBoltzmannUtils.hpp:18,125-135), speeds
+ *     0 rest, 1 E, 2 N, 3 W, 4 S, 5 NE, 6 NW, 7 SW, 8 SE; obstacles one byte per cell, non-zero =
+ *     solid, index x + y*nx (main/include/LbmParams.hpp:88-90);
+ *   - every call blocks until its work is complete (engine.run is synchronous);
+ *   - return 0 on success, a negative LBM_E_* code otherwise; the message for the calling thread's
+ *     last failure is lbm_last_error().  Nothing throws across the ABI;
+ *   - a handle is not thread-safe (the reference is single-threaded);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ *     LBM_E_CUDA.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+enum {
+  LBM_OK = 0,
+  LBM_E_ARG = -1,    /* bad argument (null pointer, non-positive size, iters beyond max_iters ...) */
+  LBM_E_CUDA = -2,   /* CUDA runtime/driver error, or no CUDA device                              */
+  LBM_E_STATE = -3,  /* call out of order (run before upload, connect twice ...)                  */
+  LBM_E_NOMEM = -4,  /* host or device allocation failed                                          */
+  LBM_E_PEER = -5    /* peer access / IPC mapping between GPUs unavailable                        */
+};
+
+typedef struct lbm_handle lbm_handle;
+
+/* ------------------------------------------------------------------------------------------------
+ * The reference's operator surface (main/LbmRunner.cpp)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Engine(Executable::deserialize(exe), opts) + engine.load(device)   -- main/LbmRunner.cpp:75-96.
+ * Creates a solver for a fixed problem (what the reference bakes into the compiled graph:
+ * main/LbmPoplibs.cpp:304-348) on num_gpus GPUs of this process (-n/--num-ipus,
+ * main/LbmRunner.cpp:19); the grid is cut into num_gpus row slabs, GPU g owning global rows
+ * [g*ny/num_gpus, (g+1)*ny/num_gpus). */
+int lbm_create(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel, float omega,
+               int num_gpus);
+
+/* engine.run(0): streams ">>cells" and ">>obstacles"  -- main/LbmRunner.cpp:87-88,98-100.
+ * Resets the step counter; the next lbm_run starts at timestep 0. */
+int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles);
+
+/* engine.run(1): the whole time loop on the device -- main/LbmRunner.cpp:102-104;
+ * program = accelerate_flow once + Repeat(timesteps) (main/LbmAoS.cpp:352-356).
+ * Runs `iters` more timesteps (the reference always runs maxIters; splitting a run into several
+ * calls gives the same result).  The first call after lbm_upload first applies the one-off guarded
+ * accelerate_flow (main/LastChance.cpp:158-183, main/codelets/D2Q9Codelets.cpp:193-224). */
+int lbm_run(lbm_handle *h, int iters);
+
+/* engine.run(2): streams "<<cells" and "<<av_vel"  -- main/LbmRunner.cpp:85-86,106-108.
+ * cells_aos receives the current state, av_vels the first `steps done` entries (max_iters floats
+ * of room).  Either pointer may be NULL to skip that stream. */
+int lbm_download(lbm_handle *h, float *cells_aos, float *av_vels);
+
+/* engine.readTensor("readTimer") / getTileClockFrequency()  -- main/LbmRunner.cpp:134-144.
+ * Device-side elapsed time of the last lbm_run (CUDA events on the launching stream; with several
+ * GPUs the maximum over them). */
+int lbm_elapsed_ms(lbm_handle *h, double *ms);
+
+/* ~Engine */
+void lbm_destroy(lbm_handle *h);
+
+/* Message for the last failing call on this thread ("" if none). */
+const char *lbm_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Introspection
+ * ---------------------------------------------------------------------------------------------- */
+
+int lbm_abi_version(void);
+/* number of CUDA devices visible to this process (0 and LBM_E_CUDA when there is none) */
+int lbm_device_count(int *count);
+/* timesteps executed since the last upload */
+int lbm_steps_done(lbm_handle *h, int *steps);
+/* non-obstacle cells in the rows this handle owns (total_free_cells, main/LastChance.cpp:486-493) */
+int lbm_free_cells(lbm_handle *h, long long *count);
+/* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+int lbm_launch_count(lbm_handle *h, long long *count);
+/* name of the sweep kernel variant in use: "vec4" (nx % 128 == 0) or "scalar" */
+const char *lbm_kernel_variant(lbm_handle *h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Extensions used by the driver, the tests and bench.py (no reference counterpart)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* lbm_create with an explicit device per slab.  A device may repeat: slabs that share a device run
+ * back to back on one stream (how the multi-slab path is exercised on a single GPU). */
+int lbm_create_on_devices(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel,
+                          float omega, int num_slabs, const int *devices);
+
+/* Generate the synthetic channel of SURVEY.md 8(d) on the device instead of uploading it: solid rows 0
+ * and ny-1, i.i.d. solids with probability `solid_prob` elsewhere except on the driven row ny-2,
+ * decided by splitmix64(seed + y*nx + x); cells get Cells::initialise values
+ * (main/include/LatticeBoltzmannUtils.hpp:137-157).  Equivalent to lbm_upload of those arrays. */
+int lbm_init_synthetic(lbm_handle *h, uint64_t seed, float solid_prob);
+
+/* the rows this handle owns: global rows [row_begin, row_begin + row_count) */
+int lbm_rows(lbm_handle *h, int *row_begin, int *row_count);
+
+/* per-timestep sum of sqrtf(u_sq) over this handle's non-obstacle cells, in double (one value per
+ * step done).  av_vels[t] = (float)(sum over ranks, in rank order) / (float)(total free cells). */
+int lbm_download_tot_u(lbm_handle *h, double *tot_u);
+
+/* pinned host memory for callers that want full-speed uploads/downloads */
+void *lbm_host_alloc(size_t bytes);
+void lbm_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------------
+ * One process per GPU (torchrun): each rank owns one row slab; neighbours' lattices are mapped with
+ * CUDA IPC and the sweep kernel stores its outgoing halo rows straight into peer memory over
+ * NVLink.  Protocol:  create_rank -> ipc_export -> (all-gather the blobs) -> ipc_connect ->
+ * upload/init_synthetic -> (barrier) -> run ... ; lbm_upload/lbm_download then take/return only the
+ * owned rows: float[row_count][nx][9] and uint8[row_count][nx].
+ * ---------------------------------------------------------------------------------------------- */
+
+int lbm_create_rank(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel,
+                    float omega, int rank, int world, int device);
+size_t lbm_ipc_blob_bytes(void);
+int lbm_ipc_export(lbm_handle *h, void *blob);
+/* blobs: world * lbm_ipc_blob_bytes() bytes, rank-major */
+int lbm_ipc_connect(lbm_handle *h, const void *blobs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

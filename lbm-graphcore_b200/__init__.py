@@ -1,0 +1,225 @@
+"""lbm-graphcore_b200 -- Python face of the B200-native D2Q9-BGK solver.
+
+The product is ``liblbm_b200.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/lbm_b200.h``) plus the C++ ``lbm_runner`` driver.  This module is a thin
+ctypes binding used by the tests, ``bench.py`` and ``__graft_entry__``; it mirrors the
+reference's operator surface (main/LbmRunner.cpp:75-144 of thorbenlouw/lbm-graphcore):
+
+    solver = Solver(params, num_gpus=1)   # Engine(...) + engine.load(device)
+    solver.upload(cells, obstacles)       # engine.run(0)   ">>cells", ">>obstacles"
+    solver.run(params.max_iters)          # engine.run(1)   the whole time loop
+    cells, av_vels = solver.download()    # engine.run(2)   "<<cells", "<<av_vel"
+    solver.elapsed_ms                     # readTimer
+
+There is no CPU fallback: if the shared library is missing this module raises at import,
+and every compute call raises ``LbmError`` when no CUDA device is usable.
+
+The directory name contains a hyphen, so import it with
+``importlib.import_module("lbm-graphcore_b200")``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblbm_b200.so")
+HOST_LIB_PATH = os.path.join(_HERE, "liblbm_host.so")
+RUNNER_PATH = os.path.join(_HERE, "bin", "lbm_runner")
+
+# names every build of liblbm_b200.so must export (kept in sync with include/lbm_b200.h by
+# tests/test_abi.py, which parses the header)
+ABI_SYMBOLS = (
+    "lbm_create", "lbm_upload", "lbm_run", "lbm_download", "lbm_elapsed_ms", "lbm_destroy",
+    "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
+    "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
+    "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_create_rank", "lbm_ipc_blob_bytes",
+    "lbm_ipc_export", "lbm_ipc_connect",
+)
+
+
+class LbmError(RuntimeError):
+    """A failing call into liblbm_b200.so (carries the library's error code and message)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"liblbm_b200 error {code}: {message}")
+        self.code = code
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU implementation to fall back to."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+    P = ctypes.POINTER
+    lib.lbm_create.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int]
+    lib.lbm_create_on_devices.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int,
+                                          P(c_int)]
+    lib.lbm_create_rank.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_int,
+                                    c_int]
+    lib.lbm_upload.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.lbm_init_synthetic.argtypes = [c_void_p, ctypes.c_uint64, c_float]
+    lib.lbm_run.argtypes = [c_void_p, c_int]
+    lib.lbm_download.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.lbm_download_tot_u.argtypes = [c_void_p, c_void_p]
+    lib.lbm_elapsed_ms.argtypes = [c_void_p, P(ctypes.c_double)]
+    lib.lbm_destroy.argtypes = [c_void_p]
+    lib.lbm_destroy.restype = None
+    lib.lbm_last_error.restype = ctypes.c_char_p
+    lib.lbm_device_count.argtypes = [P(c_int)]
+    lib.lbm_steps_done.argtypes = [c_void_p, P(c_int)]
+    lib.lbm_free_cells.argtypes = [c_void_p, P(ctypes.c_longlong)]
+    lib.lbm_launch_count.argtypes = [c_void_p, P(ctypes.c_longlong)]
+    lib.lbm_kernel_variant.argtypes = [c_void_p]
+    lib.lbm_kernel_variant.restype = ctypes.c_char_p
+    lib.lbm_rows.argtypes = [c_void_p, P(c_int), P(c_int)]
+    lib.lbm_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.lbm_host_alloc.restype = c_void_p
+    lib.lbm_host_free.argtypes = [c_void_p]
+    lib.lbm_host_free.restype = None
+    lib.lbm_ipc_blob_bytes.restype = ctypes.c_size_t
+    lib.lbm_ipc_export.argtypes = [c_void_p, c_void_p]
+    lib.lbm_ipc_connect.argtypes = [c_void_p, c_void_p]
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise LbmError(rc, lib.lbm_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    """Number of CUDA devices the library can see (0 when there is none)."""
+    n = ctypes.c_int(0)
+    rc = lib.lbm_device_count(ctypes.byref(n))
+    return n.value if rc == 0 else 0
+
+
+from .problem import NSPEEDS, Params, initial_cells, load_obstacles, synthetic_obstacles  # noqa: E402,F401
+
+
+# ---------------------------------------------------------------------------------------------------
+# The solver handle
+# ---------------------------------------------------------------------------------------------------
+class Solver:
+    """One ``lbm_handle``.  ``devices`` (a list that may repeat a GPU) selects
+    ``lbm_create_on_devices``; ``rank``/``world`` select the one-process-per-GPU mode."""
+
+    def __init__(self, params: Params, num_gpus: int = 1, devices: list[int] | None = None,
+                 rank: int | None = None, world: int | None = None, device: int = 0):
+        self.params = params
+        self._h = ctypes.c_void_p()
+        p = params
+        args = (p.nx, p.ny, p.max_iters, p.density, p.accel, p.omega)
+        if rank is not None:
+            _check(lib.lbm_create_rank(ctypes.byref(self._h), *args, rank, world, device))
+        elif devices is not None:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            _check(lib.lbm_create_on_devices(ctypes.byref(self._h), *args, len(devices), arr))
+        else:
+            _check(lib.lbm_create(ctypes.byref(self._h), *args, num_gpus))
+        rb, rc = ctypes.c_int(), ctypes.c_int()
+        _check(lib.lbm_rows(self._h, ctypes.byref(rb), ctypes.byref(rc)))
+        self.row_begin, self.row_count = rb.value, rc.value
+
+    # -- lifetime -----------------------------------------------------------------------------------
+    def close(self) -> None:
+        if self._h:
+            lib.lbm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the reference's three programs -------------------------------------------------------------
+    def upload(self, cells: np.ndarray, obstacles: np.ndarray) -> None:
+        """engine.run(0).  cells float32[rows, nx, 9], obstacles uint8/bool[rows, nx] for the rows this
+        handle owns (all of them unless in rank mode)."""
+        p = self.params
+        cells = np.ascontiguousarray(cells, dtype=np.float32)
+        obstacles = np.ascontiguousarray(obstacles).astype(np.uint8, copy=False)
+        if cells.size != self.row_count * p.nx * NSPEEDS or obstacles.size != self.row_count * p.nx:
+            raise ValueError("cells/obstacles do not match the rows owned by this solver")
+        _check(lib.lbm_upload(self._h, cells.ctypes.data, obstacles.ctypes.data))
+
+    def upload_raw(self, cells_ptr: int, obstacles_ptr: int) -> None:
+        _check(lib.lbm_upload(self._h, cells_ptr, obstacles_ptr))
+
+    def init_synthetic(self, seed: int, solid_prob: float) -> None:
+        _check(lib.lbm_init_synthetic(self._h, seed, solid_prob))
+
+    def run(self, iters: int) -> None:
+        """engine.run(1): `iters` timesteps (the first call also does the one-off accelerate_flow)."""
+        _check(lib.lbm_run(self._h, iters))
+
+    def download(self, cells: bool = True, av_vels: bool = True):
+        """engine.run(2): returns (cells float32[rows, nx, 9] | None, av_vels float32[steps] | None)."""
+        p = self.params
+        c = np.empty((self.row_count, p.nx, NSPEEDS), dtype=np.float32) if cells else None
+        a = np.zeros(max(p.max_iters, 1), dtype=np.float32) if av_vels else None
+        _check(lib.lbm_download(self._h, c.ctypes.data if cells else None, a.ctypes.data if av_vels else None))
+        return c, (a[: self.steps_done] if av_vels else None)
+
+    def download_raw(self, cells_ptr: int, av_vels_ptr: int) -> None:
+        _check(lib.lbm_download(self._h, cells_ptr, av_vels_ptr))
+
+    def download_tot_u(self) -> np.ndarray:
+        t = np.zeros(max(self.steps_done, 1), dtype=np.float64)
+        _check(lib.lbm_download_tot_u(self._h, t.ctypes.data))
+        return t[: self.steps_done]
+
+    # -- introspection ------------------------------------------------------------------------------
+    @property
+    def elapsed_ms(self) -> float:
+        ms = ctypes.c_double()
+        _check(lib.lbm_elapsed_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    @property
+    def steps_done(self) -> int:
+        n = ctypes.c_int()
+        _check(lib.lbm_steps_done(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def free_cells(self) -> int:
+        n = ctypes.c_longlong()
+        _check(lib.lbm_free_cells(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def launch_count(self) -> int:
+        n = ctypes.c_longlong()
+        _check(lib.lbm_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def kernel_variant(self) -> str:
+        return lib.lbm_kernel_variant(self._h).decode()
+
+    # -- one process per GPU ------------------------------------------------------------------------
+    def ipc_export(self) -> bytes:
+        n = lib.lbm_ipc_blob_bytes()
+        buf = ctypes.create_string_buffer(n)
+        _check(lib.lbm_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_connect(self, blobs: bytes) -> None:
+        buf = ctypes.create_string_buffer(blobs, len(blobs))
+        _check(lib.lbm_ipc_connect(self._h, buf))

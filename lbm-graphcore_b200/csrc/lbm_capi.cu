@@ -1,0 +1,753 @@
+// lbm_capi.cu -- the C ABI of include/lbm_b200.h on top of the kernels in lbm_kernels.cuh.
+//
+// Mirrors the reference's Engine-as-operator surface (main/LbmRunner.cpp:75-144): create = load the
+// program for a fixed problem, upload = run(0), run = run(1), download = run(2), elapsed = readTimer.
+// There is no CPU path in this file: every compute entry point needs a CUDA device.
+#include "../../include/lbm_b200.h"
+#include "lbm_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(LBM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation
+constexpr size_t kStageBytes = 64u << 20;  // AoS staging chunk for upload/download
+
+struct Slab {
+  int device = 0;
+  int row0 = 0;  // first owned global row
+  int nyl = 0;   // owned rows
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  // one exported allocation: [lattice 0][lattice 1][flags]
+  char *base = nullptr;
+  float *buf[2] = {nullptr, nullptr};
+  int *flags = nullptr;  // [0] from_south, [1] from_north
+  // private allocations
+  uint32_t *mask = nullptr;
+  double *partials = nullptr;
+  double *tot_u = nullptr;
+  unsigned *ticket = nullptr;  // [0] grid ticket, [1..2] edge tickets
+  int *step = nullptr;         // [0] step, [1] error
+  unsigned long long *free_dev = nullptr;
+  float *stage = nullptr;
+  // neighbours (own pointers when there is a single slab)
+  float *south_buf[2] = {nullptr, nullptr};
+  float *north_buf[2] = {nullptr, nullptr};
+  int *flag_to_south = nullptr;
+  int *flag_to_north = nullptr;
+  int south_ghost_row = 0;
+  // launch configuration
+  int vec = 1;
+  dim3 block;
+  int grid = 1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long long free_cells = 0;
+};
+
+}  // namespace
+
+struct lbm_handle {
+  int nx = 0, ny = 0, max_iters = 0;
+  float density = 0, accel = 0, omega = 0;
+  int pitch = 0, rows_alloc = 0;
+  size_t plane = 0;  // floats
+  size_t lattice_bytes = 0;
+  std::vector<Slab> slabs;
+  bool multi = false;      // more than one slab in the ring
+  bool rank_mode = false;  // one process per GPU
+  int rank = 0, world = 1;
+  bool connected = false;
+  std::vector<void *> ipc_opened;
+  int cur = 0;  // which lattice holds the current state
+  int steps_done = 0;
+  bool uploaded = false;
+  bool first_run_pending = false;
+  double last_ms = 0.0;
+  long long launches = 0;
+};
+
+namespace {
+
+size_t blob_bytes() { return sizeof(cudaIpcMemHandle_t) + 4 * sizeof(int); }
+
+int pick_tx(int nx, int vec) {
+  if (vec == 4) {
+    const int lanes = nx / 4;
+    for (int tx = 256; tx >= 32; tx >>= 1)
+      if (tx <= lanes) return tx;
+    return 32;
+  }
+  int tx = 32;
+  while (tx < 256 && tx < nx) tx <<= 1;
+  return tx;
+}
+
+template <int V, bool M>
+int occupancy_blocks(int *out) {
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, lbm::sweep_kernel<V, M>, lbm::kBlockThreads, 0));
+  return LBM_OK;
+}
+
+int configure_launch(lbm_handle *h, Slab &s) {
+  s.vec = (h->nx % 128 == 0) ? 4 : 1;
+  const int tx = pick_tx(h->nx, s.vec);
+  s.block = dim3(tx, lbm::kBlockThreads / tx, 1);
+  const int tile_w = tx * s.vec;
+  const long long tiles_x = (h->nx + tile_w - 1) / tile_w;
+  const long long tiles_y = (s.nyl + (int)s.block.y - 1) / (int)s.block.y;
+  const long long ntiles = tiles_x * tiles_y;
+  int sms = 0, per_sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
+  int rc;
+  if (s.vec == 4) rc = h->multi ? occupancy_blocks<4, true>(&per_sm) : occupancy_blocks<4, false>(&per_sm);
+  else rc = h->multi ? occupancy_blocks<1, true>(&per_sm) : occupancy_blocks<1, false>(&per_sm);
+  if (rc) return rc;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = std::min<long long>(ntiles, (long long)sms * per_sm);
+  grid = std::min<long long>(grid, lbm::kMaxPartials);
+  s.grid = (int)std::max<long long>(grid, 1);
+  return LBM_OK;
+}
+
+int alloc_slab(lbm_handle *h, Slab &s) {
+  CUDA_TRY(cudaSetDevice(s.device));
+  const size_t total = 2 * h->lattice_bytes + kFlagBytes;
+  cudaError_t e = cudaMalloc((void **)&s.base, total);
+  if (e != cudaSuccess)
+    return fail(LBM_E_NOMEM, "cudaMalloc of %zu bytes for a %d-row slab failed: %s", total, s.nyl,
+                cudaGetErrorString(e));
+  s.buf[0] = reinterpret_cast<float *>(s.base);
+  s.buf[1] = reinterpret_cast<float *>(s.base + h->lattice_bytes);
+  s.flags = reinterpret_cast<int *>(s.base + 2 * h->lattice_bytes);
+  CUDA_TRY(cudaMemset(s.flags, 0, kFlagBytes));
+  const size_t mask_bytes = (size_t)h->rows_alloc * (h->pitch / 32) * sizeof(uint32_t);
+  CUDA_TRY(cudaMalloc((void **)&s.mask, mask_bytes));
+  CUDA_TRY(cudaMemset(s.mask, 0, mask_bytes));
+  CUDA_TRY(cudaMalloc((void **)&s.partials, lbm::kMaxPartials * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s.tot_u, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
+  CUDA_TRY(cudaMemset(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s.ticket, 4 * sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(s.ticket, 0, 4 * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc((void **)&s.step, 2 * sizeof(int)));
+  CUDA_TRY(cudaMemset(s.step, 0, 2 * sizeof(int)));
+  CUDA_TRY(cudaMalloc((void **)&s.free_dev, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc((void **)&s.stage, kStageBytes));
+  CUDA_TRY(cudaEventCreate(&s.ev0));
+  CUDA_TRY(cudaEventCreate(&s.ev1));
+  return LBM_OK;
+}
+
+void free_slab(Slab &s) {
+  cudaSetDevice(s.device);
+  if (s.ev0) cudaEventDestroy(s.ev0);
+  if (s.ev1) cudaEventDestroy(s.ev1);
+  cudaFree(s.stage);
+  cudaFree(s.free_dev);
+  cudaFree(s.step);
+  cudaFree(s.ticket);
+  cudaFree(s.tot_u);
+  cudaFree(s.partials);
+  cudaFree(s.mask);
+  cudaFree(s.base);
+  if (s.owns_stream && s.stream) cudaStreamDestroy(s.stream);
+}
+
+int check_problem(int nx, int ny, int max_iters, int slabs) {
+  if (nx < 1 || ny < 1) return fail(LBM_E_ARG, "grid must be at least 1x1 (got %dx%d)", nx, ny);
+  if (max_iters < 0) return fail(LBM_E_ARG, "max_iters must be >= 0 (got %d)", max_iters);
+  if (slabs < 1) return fail(LBM_E_ARG, "need at least one GPU/slab (got %d)", slabs);
+  if (ny < slabs) return fail(LBM_E_ARG, "cannot cut %d rows into %d slabs", ny, slabs);
+  if ((long long)(ny / slabs + 3) * ((nx + 31) / 32 * 32) >= (1ll << 31))
+    return fail(LBM_E_ARG, "slab of %dx%d cells exceeds 2^31 cells per plane", nx, ny / slabs + 1);
+  return LBM_OK;
+}
+
+void set_geometry(lbm_handle *h, int nx, int ny, int max_iters, float density, float accel, float omega,
+                  int ring) {
+  h->nx = nx; h->ny = ny; h->max_iters = max_iters;
+  h->density = density; h->accel = accel; h->omega = omega;
+  h->pitch = (nx + 31) / 32 * 32;
+  h->rows_alloc = (ny + ring - 1) / ring + 2;  // same on every slab so plane strides agree
+  h->plane = (size_t)h->rows_alloc * h->pitch;
+  h->lattice_bytes = h->plane * lbm::kSpeeds * sizeof(float);
+  h->multi = ring > 1;
+}
+
+lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
+  lbm::SweepArgs a{};
+  const int c = h->cur;
+  a.src = s.buf[c];
+  a.dst = s.buf[c ^ 1];
+  a.dst_south = s.south_buf[c ^ 1];
+  a.dst_north = s.north_buf[c ^ 1];
+  a.mask = s.mask;
+  a.plane = h->plane;
+  a.pitch = h->pitch;
+  a.nx = h->nx;
+  a.nyl = s.nyl;
+  const int arow = h->ny - 2;  // main/LastChance.cpp:198 (never matches when ny < 2, like the reference)
+  a.accel_row = (arow >= s.row0 && arow < s.row0 + s.nyl) ? (arow - s.row0 + 1) : -1;
+  a.south_ghost_row = s.south_ghost_row;
+  a.omega = h->omega;
+  a.one_minus_omega = 1 - h->omega;                 // main/LastChance.cpp:387
+  a.w1 = h->density * h->accel / 9.f;               // main/LastChance.cpp:158
+  a.w2 = h->density * h->accel / 36.f;              // :159
+  a.partials = s.partials;
+  a.tot_u = s.tot_u;
+  a.ticket = s.ticket;
+  a.step = s.step;
+  a.flag_from_south = s.flags + 0;
+  a.flag_from_north = s.flags + 1;
+  a.flag_to_south = s.flag_to_south;
+  a.flag_to_north = s.flag_to_north;
+  a.edge_ticket = s.ticket + 1;
+  a.error = s.step + 1;
+  return a;
+}
+
+int launch_sweep(lbm_handle *h, Slab &s) {
+  const lbm::SweepArgs a = sweep_args(h, s);
+  if (s.vec == 4) {
+    if (h->multi) lbm::sweep_kernel<4, true><<<s.grid, s.block, 0, s.stream>>>(a);
+    else lbm::sweep_kernel<4, false><<<s.grid, s.block, 0, s.stream>>>(a);
+  } else {
+    if (h->multi) lbm::sweep_kernel<1, true><<<s.grid, s.block, 0, s.stream>>>(a);
+    else lbm::sweep_kernel<1, false><<<s.grid, s.block, 0, s.stream>>>(a);
+  }
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBM_OK;
+}
+
+// wire the ring inside one process: slab i's south neighbour is i-1, north is i+1 (periodic)
+int wire_local_ring(lbm_handle *h) {
+  const int n = (int)h->slabs.size();
+  for (int i = 0; i < n; ++i) {
+    Slab &s = h->slabs[i];
+    Slab &so = h->slabs[(i + n - 1) % n];
+    Slab &no = h->slabs[(i + 1) % n];
+    for (int b = 0; b < 2; ++b) {
+      s.south_buf[b] = so.buf[b];
+      s.north_buf[b] = no.buf[b];
+    }
+    s.flag_to_south = so.flags + 1;  // its flag_from_north
+    s.flag_to_north = no.flags + 0;  // its flag_from_south
+    s.south_ghost_row = so.nyl + 1;
+  }
+  // peer access between distinct devices of neighbouring slabs
+  for (int i = 0; i < n; ++i) {
+    for (int d : {h->slabs[(i + n - 1) % n].device, h->slabs[(i + 1) % n].device}) {
+      const int me = h->slabs[i].device;
+      if (d == me) continue;
+      int can = 0;
+      CUDA_TRY(cudaDeviceCanAccessPeer(&can, me, d));
+      if (!can) return fail(LBM_E_PEER, "GPU %d cannot access GPU %d as a peer", me, d);
+      CUDA_TRY(cudaSetDevice(me));
+      cudaError_t e = cudaDeviceEnablePeerAccess(d, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess)
+        return fail(LBM_E_PEER, "cudaDeviceEnablePeerAccess(%d -> %d): %s", me, d, cudaGetErrorString(e));
+    }
+  }
+  h->connected = true;
+  return LBM_OK;
+}
+
+int reset_counters(lbm_handle *h) {
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaMemsetAsync(s.flags, 0, kFlagBytes, s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.ticket, 0, 4 * sizeof(unsigned), s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.step, 0, 2 * sizeof(int), s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double), s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.free_dev, 0, sizeof(unsigned long long), s.stream));
+  }
+  h->cur = 0;
+  h->steps_done = 0;
+  return LBM_OK;
+}
+
+int sync_all(lbm_handle *h) {
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+  }
+  return LBM_OK;
+}
+
+int finish_upload(lbm_handle *h) {
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    unsigned long long f = 0;
+    CUDA_TRY(cudaMemcpyAsync(&f, s.free_dev, sizeof f, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    s.free_cells = (long long)f;
+  }
+  h->uploaded = true;
+  h->first_run_pending = true;
+  return LBM_OK;
+}
+
+int create_common(lbm_handle **out, lbm_handle *h) {
+  for (Slab &s : h->slabs) {
+    int rc = alloc_slab(h, s);
+    if (rc) { lbm_destroy(h); return rc; }
+    rc = configure_launch(h, s);
+    if (rc) { lbm_destroy(h); return rc; }
+  }
+  *out = h;
+  return LBM_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *lbm_last_error(void) { return g_last_error.c_str(); }
+int lbm_abi_version(void) { return LBM_B200_ABI_VERSION; }
+
+int lbm_device_count(int *count) {
+  if (!count) return fail(LBM_E_ARG, "count is null");
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(LBM_E_CUDA, "no usable CUDA device: %s", cudaGetErrorString(e));
+  }
+  return LBM_OK;
+}
+
+int lbm_create_on_devices(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel,
+                          float omega, int num_slabs, const int *devices) {
+  if (!out || !devices) return fail(LBM_E_ARG, "null argument");
+  *out = nullptr;
+  int rc = check_problem(nx, ny, max_iters, num_slabs);
+  if (rc) return rc;
+  int ndev = 0;
+  rc = lbm_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev < 1) return fail(LBM_E_CUDA, "no CUDA device present; this library has no CPU path");
+  for (int i = 0; i < num_slabs; ++i)
+    if (devices[i] < 0 || devices[i] >= ndev)
+      return fail(LBM_E_ARG, "slab %d asks for GPU %d but only %d are visible", i, devices[i], ndev);
+  lbm_handle *h = new (std::nothrow) lbm_handle();
+  if (!h) return fail(LBM_E_NOMEM, "out of host memory");
+  set_geometry(h, nx, ny, max_iters, density, accel, omega, num_slabs);
+  h->slabs.resize(num_slabs);
+  for (int i = 0; i < num_slabs; ++i) {
+    Slab &s = h->slabs[i];
+    s.device = devices[i];
+    s.row0 = (int)((long long)i * ny / num_slabs);
+    s.nyl = (int)((long long)(i + 1) * ny / num_slabs) - s.row0;
+    // slabs sharing a device share one stream, so their kernels run back to back (no co-scheduling
+    // assumption between kernels that wait on each other)
+    for (int j = 0; j < i; ++j)
+      if (h->slabs[j].device == s.device) { s.stream = h->slabs[j].stream; break; }
+    if (!s.stream) {
+      cudaError_t e = cudaSetDevice(s.device);
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+      if (e != cudaSuccess) {
+        lbm_destroy(h);
+        return fail(LBM_E_CUDA, "stream creation on GPU %d: %s", s.device, cudaGetErrorString(e));
+      }
+      s.owns_stream = true;
+    }
+  }
+  rc = create_common(out, h);
+  if (rc) return rc;
+  rc = wire_local_ring(h);
+  if (rc) { lbm_destroy(h); *out = nullptr; return rc; }
+  return LBM_OK;
+}
+
+int lbm_create(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel, float omega,
+               int num_gpus) {
+  if (num_gpus < 1 || num_gpus > 64) return fail(LBM_E_ARG, "num_gpus must be in 1..64 (got %d)", num_gpus);
+  int ndev = 0;
+  int rc = lbm_device_count(&ndev);
+  if (rc) return rc;
+  if (num_gpus > ndev) return fail(LBM_E_ARG, "asked for %d GPUs but only %d are visible", num_gpus, ndev);
+  std::vector<int> dev(num_gpus);
+  for (int i = 0; i < num_gpus; ++i) dev[i] = i;
+  return lbm_create_on_devices(out, nx, ny, max_iters, density, accel, omega, num_gpus, dev.data());
+}
+
+int lbm_create_rank(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel,
+                    float omega, int rank, int world, int device) {
+  if (!out) return fail(LBM_E_ARG, "null argument");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return fail(LBM_E_ARG, "bad rank %d of %d", rank, world);
+  int rc = check_problem(nx, ny, max_iters, world);
+  if (rc) return rc;
+  int ndev = 0;
+  rc = lbm_device_count(&ndev);
+  if (rc) return rc;
+  if (device < 0 || device >= ndev) return fail(LBM_E_ARG, "GPU %d not visible (%d devices)", device, ndev);
+  lbm_handle *h = new (std::nothrow) lbm_handle();
+  if (!h) return fail(LBM_E_NOMEM, "out of host memory");
+  set_geometry(h, nx, ny, max_iters, density, accel, omega, world);
+  h->rank_mode = true;
+  h->rank = rank;
+  h->world = world;
+  h->slabs.resize(1);
+  Slab &s = h->slabs[0];
+  s.device = device;
+  s.row0 = (int)((long long)rank * ny / world);
+  s.nyl = (int)((long long)(rank + 1) * ny / world) - s.row0;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(LBM_E_CUDA, "stream creation on GPU %d: %s", device, cudaGetErrorString(e));
+  }
+  s.owns_stream = true;
+  rc = create_common(out, h);
+  if (rc) return rc;
+  if (world == 1) return wire_local_ring(h);
+  return LBM_OK;
+}
+
+size_t lbm_ipc_blob_bytes(void) { return blob_bytes(); }
+
+int lbm_ipc_export(lbm_handle *h, void *blob) {
+  if (!h || !blob) return fail(LBM_E_ARG, "null argument");
+  if (!h->rank_mode) return fail(LBM_E_STATE, "lbm_ipc_export needs a handle from lbm_create_rank");
+  Slab &s = h->slabs[0];
+  CUDA_TRY(cudaSetDevice(s.device));
+  cudaIpcMemHandle_t mh;
+  CUDA_TRY(cudaIpcGetMemHandle(&mh, s.base));
+  char *p = static_cast<char *>(blob);
+  memcpy(p, &mh, sizeof mh);
+  const int meta[4] = {h->rank, s.nyl, h->rows_alloc, h->pitch};
+  memcpy(p + sizeof mh, meta, sizeof meta);
+  return LBM_OK;
+}
+
+int lbm_ipc_connect(lbm_handle *h, const void *blobs) {
+  if (!h || !blobs) return fail(LBM_E_ARG, "null argument");
+  if (!h->rank_mode) return fail(LBM_E_STATE, "lbm_ipc_connect needs a handle from lbm_create_rank");
+  if (h->connected) return fail(LBM_E_STATE, "already connected");
+  Slab &s = h->slabs[0];
+  CUDA_TRY(cudaSetDevice(s.device));
+  const int w = h->world, south = (h->rank + w - 1) % w, north = (h->rank + 1) % w;
+  const char *all = static_cast<const char *>(blobs);
+  char *mapped[2] = {nullptr, nullptr};
+  int peer_nyl[2] = {0, 0};
+  const int peers[2] = {south, north};
+  for (int i = 0; i < 2; ++i) {
+    if (i == 1 && north == south) { mapped[1] = mapped[0]; peer_nyl[1] = peer_nyl[0]; break; }
+    const char *b = all + (size_t)peers[i] * blob_bytes();
+    cudaIpcMemHandle_t mh;
+    int meta[4];
+    memcpy(&mh, b, sizeof mh);
+    memcpy(meta, b + sizeof mh, sizeof meta);
+    if (meta[0] != peers[i] || meta[2] != h->rows_alloc || meta[3] != h->pitch)
+      return fail(LBM_E_ARG, "IPC blob %d does not describe rank %d of the same problem", peers[i], peers[i]);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return fail(LBM_E_PEER, "cudaIpcOpenMemHandle for rank %d: %s", peers[i], cudaGetErrorString(e));
+    h->ipc_opened.push_back(ptr);
+    mapped[i] = static_cast<char *>(ptr);
+    peer_nyl[i] = meta[1];
+  }
+  for (int b = 0; b < 2; ++b) {
+    s.south_buf[b] = reinterpret_cast<float *>(mapped[0] + (size_t)b * h->lattice_bytes);
+    s.north_buf[b] = reinterpret_cast<float *>(mapped[1] + (size_t)b * h->lattice_bytes);
+  }
+  s.flag_to_south = reinterpret_cast<int *>(mapped[0] + 2 * h->lattice_bytes) + 1;
+  s.flag_to_north = reinterpret_cast<int *>(mapped[1] + 2 * h->lattice_bytes) + 0;
+  s.south_ghost_row = peer_nyl[0] + 1;
+  h->connected = true;
+  return LBM_OK;
+}
+
+void lbm_destroy(lbm_handle *h) {
+  if (!h) return;
+  for (Slab &s : h->slabs) {
+    cudaSetDevice(s.device);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+  }
+  if (!h->slabs.empty()) cudaSetDevice(h->slabs[0].device);
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  for (Slab &s : h->slabs) free_slab(s);
+  cudaGetLastError();
+  delete h;
+}
+
+// ---- run(0) --------------------------------------------------------------------------------------
+int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles) {
+  if (!h || !cells_aos || !obstacles) return fail(LBM_E_ARG, "null argument");
+  if (!h->connected) return fail(LBM_E_STATE, "ranks are not connected yet (lbm_ipc_connect)");
+  int rc = reset_counters(h);
+  if (rc) return rc;
+  const int nx = h->nx;
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    // in rank mode the caller passes only the owned rows
+    const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
+    const float *cells = cells_aos + first * nx * lbm::kSpeeds;
+    const uint8_t *obst = obstacles + first * nx;
+    // cells: AoS chunks of whole rows through the staging buffer
+    const int rows_per_chunk = (int)std::max<size_t>(1, kStageBytes / ((size_t)nx * lbm::kSpeeds * sizeof(float)));
+    if ((size_t)nx * lbm::kSpeeds * sizeof(float) > kStageBytes)
+      return fail(LBM_E_ARG, "a single row of %d cells does not fit the staging buffer", nx);
+    const int chunks_x = (nx + lbm::kBlockThreads - 1) / lbm::kBlockThreads;
+    for (int r = 0; r < s.nyl; r += rows_per_chunk) {
+      const int rows = std::min(rows_per_chunk, s.nyl - r);
+      const size_t bytes = (size_t)rows * nx * lbm::kSpeeds * sizeof(float);
+      CUDA_TRY(cudaMemcpyAsync(s.stage, cells + (size_t)r * nx * lbm::kSpeeds, bytes, cudaMemcpyHostToDevice, s.stream));
+      lbm::aos_to_soa_kernel<<<rows * chunks_x, lbm::kBlockThreads, 0, s.stream>>>(s.stage, s.buf[0], h->plane,
+                                                                                 h->pitch, nx, rows, 1 + r);
+      ++h->launches;
+      CUDA_TRY(cudaGetLastError());
+      // the staging buffer is reused: wait for the transposition before the next copy lands (a pageable
+      // source makes the copy synchronous anyway)
+      CUDA_TRY(cudaStreamSynchronize(s.stream));
+    }
+    // obstacles: bytes -> bits
+    const int rows_per_mchunk = (int)std::max<size_t>(1, kStageBytes / (size_t)nx);
+    const int words = (nx + 31) / 32;
+    uint8_t *stage8 = reinterpret_cast<uint8_t *>(s.stage);
+    for (int r = 0; r < s.nyl; r += rows_per_mchunk) {
+      const int rows = std::min(rows_per_mchunk, s.nyl - r);
+      CUDA_TRY(cudaMemcpyAsync(stage8, obst + (size_t)r * nx, (size_t)rows * nx, cudaMemcpyHostToDevice, s.stream));
+      const long long threads = (long long)rows * words * 32;
+      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(stage8, s.mask, h->pitch, nx,
+                                                                                  rows, 1 + r, s.free_dev);
+      ++h->launches;
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(s.stream));
+    }
+  }
+  return finish_upload(h);
+}
+
+int lbm_init_synthetic(lbm_handle *h, uint64_t seed, float solid_prob) {
+  if (!h) return fail(LBM_E_ARG, "null argument");
+  if (!(solid_prob >= 0.f && solid_prob <= 1.f)) return fail(LBM_E_ARG, "solid_prob must be in [0,1]");
+  if (!h->connected) return fail(LBM_E_STATE, "ranks are not connected yet (lbm_ipc_connect)");
+  int rc = reset_counters(h);
+  if (rc) return rc;
+  const uint32_t threshold24 = (uint32_t)((double)solid_prob * 16777216.0);
+  // Cells::initialise, main/include/LatticeBoltzmannUtils.hpp:137-140
+  const float w0 = h->density * 4.f / 9.f, w1 = h->density / 9.f, w2 = h->density / 36.f;
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    lbm::fill_planes_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[0], h->plane, w0, w1, w2);
+    const int words = (h->nx + 31) / 32;
+    const long long threads = (long long)s.nyl * words * 32;
+    lbm::synthetic_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
+        s.mask, h->pitch, h->nx, h->ny, s.row0, s.nyl, seed, threshold24, s.free_dev);
+    h->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return finish_upload(h);
+}
+
+// ---- run(1) --------------------------------------------------------------------------------------
+int lbm_run(lbm_handle *h, int iters) {
+  if (!h) return fail(LBM_E_ARG, "null argument");
+  if (!h->uploaded) return fail(LBM_E_STATE, "lbm_run before lbm_upload");
+  if (iters < 0 || h->steps_done + iters > h->max_iters)
+    return fail(LBM_E_ARG, "cannot run %d more steps: %d of max_iters=%d already done", iters, h->steps_done,
+                h->max_iters);
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
+  }
+  if (h->first_run_pending) {
+    // accelerate_flow once before step 0 (main/LbmAoS.cpp:352; main/LastChance.cpp:158-183) ...
+    const float w1 = h->density * h->accel / 9.f, w2 = h->density * h->accel / 36.f;
+    const int arow = h->ny - 2;
+    for (Slab &s : h->slabs) {
+      if (arow < s.row0 || arow >= s.row0 + s.nyl) continue;
+      CUDA_TRY(cudaSetDevice(s.device));
+      lbm::accelerate_flow_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
+          s.buf[h->cur], h->plane, h->pitch, h->nx, arow - s.row0 + 1, s.mask, w1, w2);
+      ++h->launches;
+      CUDA_TRY(cudaGetLastError());
+    }
+    // ... then the initial halo: every slab fills its neighbours' ghost rows and publishes epoch 1
+    for (Slab &s : h->slabs) {
+      CUDA_TRY(cudaSetDevice(s.device));
+      lbm::push_halo_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
+          s.buf[h->cur], s.north_buf[h->cur], s.south_buf[h->cur], h->plane, h->pitch, h->nx, s.nyl,
+          s.south_ghost_row);
+      ++h->launches;
+      if (h->multi) {
+        lbm::publish_epoch_kernel<<<1, 1, 0, s.stream>>>(s.flag_to_south, s.flag_to_north, 1);
+        ++h->launches;
+      }
+      CUDA_TRY(cudaGetLastError());
+    }
+    h->first_run_pending = false;
+  }
+  // one launch per slab per timestep, slabs interleaved so no GPU's queue runs ahead of its neighbours
+  for (int t = 0; t < iters; ++t) {
+    for (Slab &s : h->slabs) {
+      if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
+      int rc = launch_sweep(h, s);
+      if (rc) return rc;
+    }
+    h->cur ^= 1;
+  }
+  h->steps_done += iters;
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaEventRecord(s.ev1, s.stream));
+  }
+  double ms_max = 0.0;
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    cudaError_t e = cudaEventSynchronize(s.ev1);
+    if (e != cudaSuccess) {
+      int err[2] = {0, 0};
+      cudaMemcpy(err, s.step, sizeof err, cudaMemcpyDeviceToHost);
+      return fail(LBM_E_CUDA, "time loop failed on GPU %d: %s%s", s.device, cudaGetErrorString(e),
+                  err[1] ? " (timed out waiting for a neighbour slab's halo)" : "");
+    }
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+    ms_max = std::max(ms_max, (double)ms);
+  }
+  h->last_ms = ms_max;
+  return LBM_OK;
+}
+
+int lbm_elapsed_ms(lbm_handle *h, double *ms) {
+  if (!h || !ms) return fail(LBM_E_ARG, "null argument");
+  *ms = h->last_ms;
+  return LBM_OK;
+}
+
+// ---- run(2) --------------------------------------------------------------------------------------
+int lbm_download_tot_u(lbm_handle *h, double *tot_u) {
+  if (!h || !tot_u) return fail(LBM_E_ARG, "null argument");
+  if (!h->uploaded) return fail(LBM_E_STATE, "nothing uploaded");
+  std::vector<double> part(h->steps_done);
+  for (int t = 0; t < h->steps_done; ++t) tot_u[t] = 0.0;
+  // slabs are added in slab order: the documented, deterministic reduction order
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (h->steps_done)
+      CUDA_TRY(cudaMemcpy(part.data(), s.tot_u, (size_t)h->steps_done * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < h->steps_done; ++t) tot_u[t] += part[t];
+  }
+  return LBM_OK;
+}
+
+int lbm_download(lbm_handle *h, float *cells_aos, float *av_vels) {
+  if (!h) return fail(LBM_E_ARG, "null argument");
+  if (!h->uploaded) return fail(LBM_E_STATE, "lbm_download before lbm_upload");
+  if (av_vels && h->rank_mode && h->world > 1)
+    return fail(LBM_E_ARG, "with one process per GPU av_vels needs all ranks: use lbm_download_tot_u and "
+                           "combine in rank order");
+  const int nx = h->nx;
+  if (cells_aos) {
+    for (Slab &s : h->slabs) {
+      CUDA_TRY(cudaSetDevice(s.device));
+      const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
+      float *cells = cells_aos + first * nx * lbm::kSpeeds;
+      const int rows_per_chunk = (int)std::max<size_t>(1, kStageBytes / ((size_t)nx * lbm::kSpeeds * sizeof(float)));
+      const int chunks_x = (nx + lbm::kBlockThreads - 1) / lbm::kBlockThreads;
+      for (int r = 0; r < s.nyl; r += rows_per_chunk) {
+        const int rows = std::min(rows_per_chunk, s.nyl - r);
+        const size_t bytes = (size_t)rows * nx * lbm::kSpeeds * sizeof(float);
+        lbm::soa_to_aos_kernel<<<rows * chunks_x, lbm::kBlockThreads, 0, s.stream>>>(s.buf[h->cur], s.stage, h->plane,
+                                                                                   h->pitch, nx, rows, 1 + r);
+        ++h->launches;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(cells + (size_t)r * nx * lbm::kSpeeds, s.stage, bytes, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+      }
+    }
+  }
+  if (av_vels) {
+    std::vector<double> tot(std::max(h->steps_done, 1));
+    int rc = lbm_download_tot_u(h, tot.data());
+    if (rc) return rc;
+    long long free_cells = 0;
+    for (Slab &s : h->slabs) free_cells += s.free_cells;
+    // main/LastChance.cpp:266: fp32 quotient of the total by the fp32 free-cell count
+    for (int t = 0; t < h->steps_done; ++t) av_vels[t] = (float)tot[t] / (float)free_cells;
+  }
+  return LBM_OK;
+}
+
+// ---- introspection -------------------------------------------------------------------------------
+int lbm_steps_done(lbm_handle *h, int *steps) {
+  if (!h || !steps) return fail(LBM_E_ARG, "null argument");
+  *steps = h->steps_done;
+  return LBM_OK;
+}
+int lbm_free_cells(lbm_handle *h, long long *count) {
+  if (!h || !count) return fail(LBM_E_ARG, "null argument");
+  if (!h->uploaded) return fail(LBM_E_STATE, "nothing uploaded");
+  *count = 0;
+  for (Slab &s : h->slabs) *count += s.free_cells;
+  return LBM_OK;
+}
+int lbm_launch_count(lbm_handle *h, long long *count) {
+  if (!h || !count) return fail(LBM_E_ARG, "null argument");
+  *count = h->launches;
+  return LBM_OK;
+}
+const char *lbm_kernel_variant(lbm_handle *h) {
+  if (!h || h->slabs.empty()) return "";
+  return h->slabs[0].vec == 4 ? "vec4" : "scalar";
+}
+int lbm_rows(lbm_handle *h, int *row_begin, int *row_count) {
+  if (!h || !row_begin || !row_count) return fail(LBM_E_ARG, "null argument");
+  if (h->rank_mode) {
+    *row_begin = h->slabs[0].row0;
+    *row_count = h->slabs[0].nyl;
+  } else {
+    *row_begin = 0;
+    *row_count = h->ny;
+  }
+  return LBM_OK;
+}
+
+void *lbm_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    fail(LBM_E_NOMEM, "cudaMallocHost(%zu) failed", bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void lbm_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+"""GPU parity: the CUDA path, called through the C ABI (liblbm_b200.so), against the CPU oracle.
+
+Bar (integer/bit work is n/a here; this is fp32): the lattice must be BIT-EXACT -- the kernels issue
+every fp32 operation as an explicit round-to-nearest intrinsic in the reference's order and the
+oracle is compiled with -ffp-contract=off.  av_vels is a sum whose order differs (GPU: fp64 tree,
+oracle: fp64 row-major), so it is compared after rounding to fp32 with a tolerance of 1 ulp."""
+import numpy as np
+import pytest
+
+from conftest import CASES, obstacles_path, params_path, ulp_distance
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_problem(oracle, lbm, nx, ny, iters, seed, solid_frac=0.05, accel=0.005):
+    rng = np.random.default_rng(seed)
+    p = lbm.Params(nx, ny, iters, 10, 0.1, accel, 1.85)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, accel, 1.85)
+    obst = (rng.random((ny, nx)) < solid_frac).astype(np.uint8)
+    # perturbed initial state so that every population differs from cell to cell
+    cells = lbm.initial_cells(p) * (1.0 + 0.1 * rng.random((ny, nx, 9))).astype(np.float32)
+    return p, op, cells.astype(np.float32), obst
+
+
+def _assert_matches_oracle(oracle, lbm, p, op, cells, obst, iters, **solver_kw):
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    with lbm.Solver(p, **solver_kw) as s:
+        s.upload(cells, obst)
+        s.run(iters)
+        got_cells, got_av = s.download()
+        assert s.free_cells == int((obst == 0).sum())
+    assert got_cells.shape == want_cells.shape
+    mism = np.flatnonzero(got_cells.view(np.uint32) != want_cells.view(np.uint32))
+    assert mism.size == 0, f"{mism.size} lattice values differ from the oracle (first flat index {mism[0]})"
+    assert np.all(np.isfinite(got_av))
+    assert ulp_distance(got_av, want_av).max() <= 1
+    return got_cells, got_av
+
+
+@pytest.mark.parametrize("case", ["128x128", "128x256"])
+def test_shipped_inputs_bit_exact_short(oracle, lbm, case):
+    """vec4 kernel on the reference's own inputs, 1500 steps, bit-exact lattice."""
+    p = lbm.Params.from_file(params_path(case))
+    op = oracle.load_params(params_path(case))
+    obst = lbm.load_obstacles(p.nx, p.ny, obstacles_path(case))
+    assert np.array_equal(obst, oracle.load_obstacles(obstacles_path(case), p.nx, p.ny))
+    with lbm.Solver(p) as s:
+        assert s.kernel_variant == "vec4"
+    _assert_matches_oracle(oracle, lbm, p, op, lbm.initial_cells(p), obst, 1500)
+
+
+@pytest.mark.parametrize("nx,ny", [(100, 37), (3, 2), (1, 1), (31, 5), (257, 3), (130, 64)])
+def test_scalar_kernel_ragged_sizes(oracle, lbm, nx, ny):
+    """Sizes the float4 path cannot take (nx % 128 != 0), including the reference KAT shape 3x2 and 1x1."""
+    p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 40, seed=nx * 1000 + ny)
+    with lbm.Solver(p) as s:
+        assert s.kernel_variant == "scalar"
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 40)
+
+
+@pytest.mark.parametrize("nx,ny", [(128, 1), (128, 2), (256, 7), (1024, 33), (2048, 16), (384, 9)])
+def test_vec4_kernel_random(oracle, lbm, nx, ny):
+    """float4 path with random solids everywhere (also on the driven row) and a perturbed lattice."""
+    p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 30, seed=nx + ny, solid_frac=0.1)
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30)
+
+
+def test_run_in_pieces_equals_one_run(oracle, lbm):
+    p, op, cells, obst = _random_problem(oracle, lbm, 256, 64, 50, seed=7)
+    want_cells, want_av = oracle.run(op, cells, obst, 50, accum=oracle.ACCUM_DOUBLE)
+    with lbm.Solver(p) as s:
+        s.upload(cells, obst)
+        for n in (1, 2, 17, 30):
+            s.run(n)
+        got_cells, got_av = s.download()
+        assert s.steps_done == 50
+    assert np.array_equal(got_cells.view(np.uint32), want_cells.view(np.uint32))
+    assert ulp_distance(got_av, want_av).max() <= 1
+    # odd number of steps: the state lives in the other buffer
+    want_cells, _ = oracle.run(op, cells, obst, 33, accum=oracle.ACCUM_DOUBLE)
+    with lbm.Solver(p) as s:
+        s.upload(cells, obst)
+        s.run(33)
+        got_cells, _ = s.download()
+    assert np.array_equal(got_cells.view(np.uint32), want_cells.view(np.uint32))
+
+
+@pytest.mark.parametrize("slabs", [2, 3, 4])
+@pytest.mark.parametrize("nx,ny", [(256, 64), (100, 19)])
+def test_multi_slab_on_one_gpu_bit_exact(oracle, lbm, slabs, nx, ny):
+    """Row-slab decomposition with writer-filled ghost rows and epoch flags, all slabs on GPU 0 (kernels
+    run back to back on one stream).  The lattice must not depend on the decomposition."""
+    p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 25, seed=slabs)
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 25, devices=[0] * slabs)
+
+
+def test_synthetic_channel_matches_host_twin(oracle, lbm):
+    """lbm_init_synthetic == uploading the numpy twin of the same mask + Cells::initialise."""
+    nx, ny, iters = 1024, 96, 12
+    p = lbm.Params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    obst = lbm.synthetic_obstacles(nx, ny, seed=1234, solid_prob=0.01)
+    assert obst[0].all() and obst[-1].all() and not obst[ny - 2].any()
+    assert 0.005 < obst[1:-2].mean() < 0.015
+    want_cells, want_av = oracle.run(op, lbm.initial_cells(p), obst, iters, accum=oracle.ACCUM_DOUBLE)
+    with lbm.Solver(p) as s:
+        s.init_synthetic(1234, 0.01)
+        assert s.free_cells == int((obst == 0).sum())
+        s.run(iters)
+        got_cells, got_av = s.download()
+    assert np.array_equal(got_cells.view(np.uint32), want_cells.view(np.uint32))
+    assert ulp_distance(got_av, want_av).max() <= 1
+
+
+def test_errors_are_reported_not_thrown(lbm):
+    p = lbm.Params(128, 128, 10, 10, 0.1, 0.005, 1.85)
+    with lbm.Solver(p) as s:
+        with pytest.raises(lbm.LbmError) as e:
+            s.run(1)  # before upload
+        assert e.value.code == -3
+        s.upload(lbm.initial_cells(p), np.zeros((128, 128), np.uint8))
+        with pytest.raises(lbm.LbmError) as e:
+            s.run(11)  # beyond max_iters
+        assert e.value.code == -1
+    with pytest.raises(lbm.LbmError):
+        lbm.Solver(lbm.Params(0, 5, 1, 1, 0.1, 0.005, 1.85))
+    with pytest.raises(lbm.LbmError):
+        lbm.Solver(p, num_gpus=1000)
