@@ -66,6 +66,7 @@ struct Slab {
   int vec = 1;
   dim3 block;
   int grid = 1;
+  int rows_iter = 1;  // rows each thread walks per tile
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long free_cells = 0;
 };
@@ -118,10 +119,6 @@ int configure_launch(lbm_handle *h, Slab &s) {
   s.vec = (h->nx % 128 == 0) ? 4 : 1;
   const int tx = pick_tx(h->nx, s.vec);
   s.block = dim3(tx, lbm::kBlockThreads / tx, 1);
-  const int tile_w = tx * s.vec;
-  const long long tiles_x = (h->nx + tile_w - 1) / tile_w;
-  const long long tiles_y = (s.nyl + (int)s.block.y - 1) / (int)s.block.y;
-  const long long ntiles = tiles_x * tiles_y;
   int sms = 0, per_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
   int rc;
@@ -129,8 +126,17 @@ int configure_launch(lbm_handle *h, Slab &s) {
   else rc = h->multi ? occupancy_blocks<1, true>(&per_sm) : occupancy_blocks<1, false>(&per_sm);
   if (rc) return rc;
   if (per_sm < 1) per_sm = 1;
-  long long grid = std::min<long long>(ntiles, (long long)sms * per_sm);
-  grid = std::min<long long>(grid, lbm::kMaxPartials);
+  const long long resident = std::min<long long>((long long)sms * per_sm, lbm::kMaxPartials);
+  // tile height: as many rows per thread as still leaves >= 64 tiles per resident block (tail balance)
+  const int tile_w = tx * s.vec;
+  const long long tiles_x = (h->nx + tile_w - 1) / tile_w;
+  long long ntiles = 0;
+  for (s.rows_iter = 16; s.rows_iter >= 1; s.rows_iter >>= 1) {
+    const int tile_h = (int)s.block.y * s.rows_iter;
+    ntiles = tiles_x * ((s.nyl + tile_h - 1) / tile_h);
+    if (ntiles >= 64 * resident || s.rows_iter == 1) break;
+  }
+  long long grid = std::min<long long>(ntiles, resident);
   s.grid = (int)std::max<long long>(grid, 1);
   return LBM_OK;
 }
@@ -202,18 +208,22 @@ void set_geometry(lbm_handle *h, int nx, int ny, int max_iters, float density, f
 lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   lbm::SweepArgs a{};
   const int c = h->cur;
-  a.src = s.buf[c];
-  a.dst = s.buf[c ^ 1];
-  a.dst_south = s.south_buf[c ^ 1];
-  a.dst_north = s.north_buf[c ^ 1];
+  static const int north_planes[3] = {2, 5, 6}, south_planes[3] = {4, 7, 8};
+  for (int k = 0; k < lbm::kSpeeds; ++k) {
+    a.src[k] = s.buf[c] + (size_t)k * h->plane;
+    a.dst[k] = s.buf[c ^ 1] + (size_t)k * h->plane;
+  }
+  for (int i = 0; i < 3; ++i) {
+    a.ghost_north[i] = s.north_buf[c ^ 1] + (size_t)north_planes[i] * h->plane;  // storage row 0
+    a.ghost_south[i] = s.south_buf[c ^ 1] + (size_t)south_planes[i] * h->plane + (size_t)s.south_ghost_row * h->pitch;
+  }
   a.mask = s.mask;
-  a.plane = h->plane;
   a.pitch = h->pitch;
   a.nx = h->nx;
   a.nyl = s.nyl;
   const int arow = h->ny - 2;  // main/LastChance.cpp:198 (never matches when ny < 2, like the reference)
   a.accel_row = (arow >= s.row0 && arow < s.row0 + s.nyl) ? (arow - s.row0 + 1) : -1;
-  a.south_ghost_row = s.south_ghost_row;
+  a.rows_iter = s.rows_iter;
   a.omega = h->omega;
   a.one_minus_omega = 1 - h->omega;                 // main/LastChance.cpp:387
   a.w1 = h->density * h->accel / 9.f;               // main/LastChance.cpp:158
