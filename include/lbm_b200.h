@@ -95,7 +95,8 @@ int lbm_steps_done(lbm_handle *h, int *steps);
 int lbm_free_cells(lbm_handle *h, long long *count);
 /* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int lbm_launch_count(lbm_handle *h, long long *count);
-/* name of the sweep kernel variant in use: "vec4" (nx % 128 == 0) or "scalar" */
+/* name of the sweep kernel variant in use: "tma" (nx % 128 == 0), "scalar" (any nx), or "vec4" (the
+ * register-path float4 kernel, selectable with LBM_B200_KERNEL=ldg for comparison runs) */
 const char *lbm_kernel_variant(lbm_handle *h);
 
 /* ------------------------------------------------------------------------------------------------
@@ -119,6 +120,11 @@ int lbm_rows(lbm_handle *h, int *row_begin, int *row_count);
 /* per-timestep sum of sqrtf(u_sq) over this handle's non-obstacle cells, in double (one value per
  * step done).  av_vels[t] = (float)(sum over ranks, in rank order) / (float)(total free cells). */
 int lbm_download_tot_u(lbm_handle *h, double *tot_u);
+
+/* Self-test of the kernels' IEEE division / square-root helpers against CUDA's __fdiv_rn / __fsqrt_rn on
+ * GPU `device`: exhaustive for x/9, x/36 and sqrt(x), `pairs` random operand pairs for a/b.
+ * counts[7] = {x/9 mismatches, sqrt mismatches, a/b mismatches, x/36 mismatches, #x/9, #sqrt, #a/b}. */
+int lbm_selftest_math(int device, unsigned long long pairs, unsigned long long *counts);
 
 /* pinned host memory for callers that want full-speed uploads/downloads */
 void *lbm_host_alloc(size_t bytes);

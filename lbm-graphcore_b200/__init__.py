@@ -24,7 +24,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblbm_b200.so")
+LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "liblbm_b200.so")  # override: kernel tuning builds
 HOST_LIB_PATH = os.path.join(_HERE, "liblbm_host.so")
 RUNNER_PATH = os.path.join(_HERE, "bin", "lbm_runner")
 
@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_create_rank", "lbm_ipc_blob_bytes",
-    "lbm_ipc_export", "lbm_ipc_connect",
+    "lbm_ipc_export", "lbm_ipc_connect", "lbm_selftest_math",
 )
 
 
@@ -84,6 +84,7 @@ def _load() -> ctypes.CDLL:
     lib.lbm_ipc_blob_bytes.restype = ctypes.c_size_t
     lib.lbm_ipc_export.argtypes = [c_void_p, c_void_p]
     lib.lbm_ipc_connect.argtypes = [c_void_p, c_void_p]
+    lib.lbm_selftest_math.argtypes = [c_int, ctypes.c_ulonglong, P(ctypes.c_ulonglong)]
     return lib
 
 
@@ -93,6 +94,14 @@ lib = _load()
 def _check(rc: int) -> None:
     if rc != 0:
         raise LbmError(rc, lib.lbm_last_error().decode("utf-8", "replace"))
+
+
+def selftest_math(device: int = 0, pairs: int = 1 << 32) -> dict:
+    """Compare the kernels' division / sqrt helpers with CUDA's IEEE library calls on the GPU."""
+    c = (ctypes.c_ulonglong * 7)()
+    _check(lib.lbm_selftest_math(device, pairs, c))
+    return {"div9_bad": c[0], "sqrt_bad": c[1], "div_bad": c[2], "div36_bad": c[3], "div9_n": c[4], "sqrt_n": c[5],
+            "div_n": c[6]}
 
 
 def device_count() -> int:

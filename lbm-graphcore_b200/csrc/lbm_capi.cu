@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -33,6 +34,15 @@ int fail(int code, const char *fmt, ...) {
     cudaError_t e_ = (expr);                                                                             \
     if (e_ != cudaSuccess)                                                                               \
       return fail(LBM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+enum { KERNEL_SCALAR = 0, KERNEL_LDG4 = 1, KERNEL_TMA = 2 };
+// LBM_B200_DEBUG_SYNC=1: synchronise after every kernel launch and name the kernel that failed
+#define KERNEL_CHECK(stream, name)                                                                      \
+  do {                                                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                                 \
+    if (e_ == cudaSuccess && getenv("LBM_B200_DEBUG_SYNC")) e_ = cudaStreamSynchronize(stream);          \
+    if (e_ != cudaSuccess) return fail(LBM_E_CUDA, "kernel %s failed: %s", name, cudaGetErrorString(e_)); \
   } while (0)
 
 constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation
@@ -63,10 +73,13 @@ struct Slab {
   int *flag_to_north = nullptr;
   int south_ghost_row = 0;
   // launch configuration
-  int vec = 1;
+  int kernel = 0;  // KERNEL_SCALAR / KERNEL_LDG4 / KERNEL_TMA
   dim3 block;
   int grid = 1;
-  int rows_iter = 1;  // rows each thread walks per tile
+  int rows_iter = 1;   // LDG kernels: rows each thread walks per tile
+  int stages = 0;      // TMA kernel: pipeline depth
+  size_t dyn_smem = 0; // TMA kernel: bytes of dynamic shared memory
+  CUtensorMap tmap[2][2]; // TMA kernel: 3-D maps (x, row, plane) per lattice buffer: [buffer][narrow|wide box]
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long free_cells = 0;
 };
@@ -76,7 +89,7 @@ struct Slab {
 struct lbm_handle {
   int nx = 0, ny = 0, max_iters = 0;
   float density = 0, accel = 0, omega = 0;
-  int pitch = 0, rows_alloc = 0;
+  int pitch = 0, mask_pitch = 0, rows_alloc = 0;
   size_t plane = 0;  // floats
   size_t lattice_bytes = 0;
   std::vector<Slab> slabs;
@@ -97,6 +110,31 @@ namespace {
 
 size_t blob_bytes() { return sizeof(cudaIpcMemHandle_t) + 4 * sizeof(int); }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_lattice_map(lbm_handle *h, float *buf, int box_w, int box_h, CUtensorMap *out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(LBM_E_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)h->pitch, (cuuint64_t)h->rows_alloc, (cuuint64_t)lbm::kSpeeds};
+  const cuuint64_t strides[2] = {(cuuint64_t)h->pitch * sizeof(float), (cuuint64_t)h->plane * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LBM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return LBM_OK;
+}
+
 int pick_tx(int nx, int vec) {
   if (vec == 4) {
     const int lanes = nx / 4;
@@ -109,26 +147,63 @@ int pick_tx(int nx, int vec) {
   return tx;
 }
 
-template <int V, bool M>
-int occupancy_blocks(int *out) {
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, lbm::sweep_kernel<V, M>, lbm::kBlockThreads, 0));
+template <typename K>
+int occupancy_blocks(K kernel, size_t dyn_smem, int *out) {
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, lbm::kBlockThreads, dyn_smem));
   return LBM_OK;
 }
 
+int env_int(const char *name, int fallback) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : fallback;
+}
+
+// Choose the sweep kernel and its launch shape for one slab.  Called after alloc_slab.
 int configure_launch(lbm_handle *h, Slab &s) {
-  s.vec = (h->nx % 128 == 0) ? 4 : 1;
-  const int tx = pick_tx(h->nx, s.vec);
-  s.block = dim3(tx, lbm::kBlockThreads / tx, 1);
-  int sms = 0, per_sm = 0;
+  CUDA_TRY(cudaSetDevice(s.device));
+  int sms = 0, per_sm = 0, rc = LBM_OK;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
-  int rc;
-  if (s.vec == 4) rc = h->multi ? occupancy_blocks<4, true>(&per_sm) : occupancy_blocks<4, false>(&per_sm);
-  else rc = h->multi ? occupancy_blocks<1, true>(&per_sm) : occupancy_blocks<1, false>(&per_sm);
+  s.kernel = (h->nx % 128 == 0) ? KERNEL_TMA : KERNEL_SCALAR;
+  // development knob (profiling sweeps): LBM_B200_KERNEL=ldg forces the register-path float4 kernel
+  if (const char *e = getenv("LBM_B200_KERNEL"))
+    if (s.kernel == KERNEL_TMA && !strcmp(e, "ldg")) s.kernel = KERNEL_LDG4;
+
+  if (s.kernel == KERNEL_TMA) {
+    s.block = dim3(32, lbm::kUnitH, 1);  // one warp per row of a 128 x 8 unit
+    s.stages = std::max(2, std::min(lbm::kMaxStages, env_int("LBM_B200_STAGES", 4)));
+    s.dyn_smem = (size_t)s.stages * lbm::kStageFloats * sizeof(float);
+    if (h->multi) {
+      CUDA_TRY(cudaFuncSetAttribute(lbm::sweep_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.dyn_smem));
+      rc = occupancy_blocks(lbm::sweep_tma_kernel<true>, s.dyn_smem, &per_sm);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(lbm::sweep_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.dyn_smem));
+      rc = occupancy_blocks(lbm::sweep_tma_kernel<false>, s.dyn_smem, &per_sm);
+    }
+    if (rc) return rc;
+    for (int b = 0; b < 2; ++b) {
+      rc = encode_lattice_map(h, s.buf[b], lbm::kUnitW, lbm::kUnitH, &s.tmap[b][0]);
+      if (!rc) rc = encode_lattice_map(h, s.buf[b], lbm::kWideW, lbm::kUnitH, &s.tmap[b][1]);
+      if (rc) return rc;
+    }
+    // one CTA per SM: measured faster than two (profiles/): a second CTA adds no bandwidth (the copies are
+    // already `stages` deep) but its extra in-flight boxes push the shared edge sectors of neighbouring
+    // units out of L2 (+13 % DRAM reads)
+    per_sm = std::max(1, std::min(per_sm, env_int("LBM_B200_BLOCKS_PER_SM", 1)));
+    const long long units = (long long)(h->nx / lbm::kUnitW) * ((s.nyl + lbm::kUnitH - 1) / lbm::kUnitH);
+    s.grid = (int)std::max<long long>(1, std::min<long long>({units, (long long)sms * per_sm, (long long)lbm::kMaxPartials}));
+    return LBM_OK;
+  }
+
+  const int vec = s.kernel == KERNEL_LDG4 ? 4 : 1;
+  const int tx = pick_tx(h->nx, vec);
+  s.block = dim3(tx, lbm::kBlockThreads / tx, 1);
+  if (vec == 4) rc = h->multi ? occupancy_blocks(lbm::sweep_kernel<4, true>, 0, &per_sm) : occupancy_blocks(lbm::sweep_kernel<4, false>, 0, &per_sm);
+  else rc = h->multi ? occupancy_blocks(lbm::sweep_kernel<1, true>, 0, &per_sm) : occupancy_blocks(lbm::sweep_kernel<1, false>, 0, &per_sm);
   if (rc) return rc;
-  if (per_sm < 1) per_sm = 1;
+  per_sm = std::max(1, std::min(per_sm, env_int("LBM_B200_BLOCKS_PER_SM", per_sm)));
   const long long resident = std::min<long long>((long long)sms * per_sm, lbm::kMaxPartials);
   // tile height: as many rows per thread as still leaves >= 64 tiles per resident block (tail balance)
-  const int tile_w = tx * s.vec;
+  const int tile_w = tx * vec;
   const long long tiles_x = (h->nx + tile_w - 1) / tile_w;
   long long ntiles = 0;
   for (s.rows_iter = 16; s.rows_iter >= 1; s.rows_iter >>= 1) {
@@ -136,8 +211,12 @@ int configure_launch(lbm_handle *h, Slab &s) {
     ntiles = tiles_x * ((s.nyl + tile_h - 1) / tile_h);
     if (ntiles >= 64 * resident || s.rows_iter == 1) break;
   }
-  long long grid = std::min<long long>(ntiles, resident);
-  s.grid = (int)std::max<long long>(grid, 1);
+  if (const char *e = getenv("LBM_B200_ROWS_ITER")) {
+    s.rows_iter = std::max(1, atoi(e));
+    const int tile_h = (int)s.block.y * s.rows_iter;
+    ntiles = tiles_x * ((s.nyl + tile_h - 1) / tile_h);
+  }
+  s.grid = (int)std::max<long long>(std::min<long long>(ntiles, resident), 1);
   return LBM_OK;
 }
 
@@ -152,7 +231,7 @@ int alloc_slab(lbm_handle *h, Slab &s) {
   s.buf[1] = reinterpret_cast<float *>(s.base + h->lattice_bytes);
   s.flags = reinterpret_cast<int *>(s.base + 2 * h->lattice_bytes);
   CUDA_TRY(cudaMemset(s.flags, 0, kFlagBytes));
-  const size_t mask_bytes = (size_t)h->rows_alloc * (h->pitch / 32) * sizeof(uint32_t);
+  const size_t mask_bytes = (size_t)h->rows_alloc * h->mask_pitch * sizeof(uint32_t);
   CUDA_TRY(cudaMalloc((void **)&s.mask, mask_bytes));
   CUDA_TRY(cudaMemset(s.mask, 0, mask_bytes));
   CUDA_TRY(cudaMalloc((void **)&s.partials, lbm::kMaxPartials * sizeof(double)));
@@ -189,7 +268,7 @@ int check_problem(int nx, int ny, int max_iters, int slabs) {
   if (max_iters < 0) return fail(LBM_E_ARG, "max_iters must be >= 0 (got %d)", max_iters);
   if (slabs < 1) return fail(LBM_E_ARG, "need at least one GPU/slab (got %d)", slabs);
   if (ny < slabs) return fail(LBM_E_ARG, "cannot cut %d rows into %d slabs", ny, slabs);
-  if ((long long)(ny / slabs + 3) * ((nx + 31) / 32 * 32) >= (1ll << 31))
+  if ((long long)(ny / slabs + 4) * ((nx + lbm::kCol0 + 1 + 31) / 32 * 32) >= (1ll << 31))
     return fail(LBM_E_ARG, "slab of %dx%d cells exceeds 2^31 cells per plane", nx, ny / slabs + 1);
   return LBM_OK;
 }
@@ -198,32 +277,38 @@ void set_geometry(lbm_handle *h, int nx, int ny, int max_iters, float density, f
                   int ring) {
   h->nx = nx; h->ny = ny; h->max_iters = max_iters;
   h->density = density; h->accel = accel; h->omega = omega;
-  h->pitch = (nx + 31) / 32 * 32;
+  h->pitch = (nx + lbm::kCol0 + 1 + 31) / 32 * 32;  // [32 ghost/pad | nx cells | east ghost | pad]
+  h->mask_pitch = (nx + 31) / 32;
   h->rows_alloc = (ny + ring - 1) / ring + 2;  // same on every slab so plane strides agree
   h->plane = (size_t)h->rows_alloc * h->pitch;
   h->lattice_bytes = h->plane * lbm::kSpeeds * sizeof(float);
   h->multi = ring > 1;
 }
 
+// pointer to (storage row 0, column kCol0) of plane k of a lattice buffer
+inline float *plane_ptr(const lbm_handle *h, float *buf, int k) { return buf + (size_t)k * h->plane + lbm::kCol0; }
+
 lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   lbm::SweepArgs a{};
   const int c = h->cur;
   static const int north_planes[3] = {2, 5, 6}, south_planes[3] = {4, 7, 8};
   for (int k = 0; k < lbm::kSpeeds; ++k) {
-    a.src[k] = s.buf[c] + (size_t)k * h->plane;
-    a.dst[k] = s.buf[c ^ 1] + (size_t)k * h->plane;
+    a.src[k] = plane_ptr(h, s.buf[c], k);
+    a.dst[k] = plane_ptr(h, s.buf[c ^ 1], k);
   }
   for (int i = 0; i < 3; ++i) {
-    a.ghost_north[i] = s.north_buf[c ^ 1] + (size_t)north_planes[i] * h->plane;  // storage row 0
-    a.ghost_south[i] = s.south_buf[c ^ 1] + (size_t)south_planes[i] * h->plane + (size_t)s.south_ghost_row * h->pitch;
+    a.ghost_north[i] = plane_ptr(h, s.north_buf[c ^ 1], north_planes[i]);  // storage row 0
+    a.ghost_south[i] = plane_ptr(h, s.south_buf[c ^ 1], south_planes[i]) + (size_t)s.south_ghost_row * h->pitch;
   }
   a.mask = s.mask;
+  a.mask_pitch = h->mask_pitch;
   a.pitch = h->pitch;
   a.nx = h->nx;
   a.nyl = s.nyl;
   const int arow = h->ny - 2;  // main/LastChance.cpp:198 (never matches when ny < 2, like the reference)
   a.accel_row = (arow >= s.row0 && arow < s.row0 + s.nyl) ? (arow - s.row0 + 1) : -1;
   a.rows_iter = s.rows_iter;
+  a.stages = s.stages;
   a.omega = h->omega;
   a.one_minus_omega = 1 - h->omega;                 // main/LastChance.cpp:387
   a.w1 = h->density * h->accel / 9.f;               // main/LastChance.cpp:158
@@ -243,15 +328,30 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
 
 int launch_sweep(lbm_handle *h, Slab &s) {
   const lbm::SweepArgs a = sweep_args(h, s);
-  if (s.vec == 4) {
-    if (h->multi) lbm::sweep_kernel<4, true><<<s.grid, s.block, 0, s.stream>>>(a);
-    else lbm::sweep_kernel<4, false><<<s.grid, s.block, 0, s.stream>>>(a);
-  } else {
-    if (h->multi) lbm::sweep_kernel<1, true><<<s.grid, s.block, 0, s.stream>>>(a);
-    else lbm::sweep_kernel<1, false><<<s.grid, s.block, 0, s.stream>>>(a);
+  if (getenv("LBM_B200_DEBUG_ARGS")) {
+    fprintf(stderr, "[lbm] sweep kernel=%d grid=%d block=(%u,%u) smem=%zu base=%p bytes=%zu buf0=%p buf1=%p plane=%zu pitch=%d "
+            "mask_pitch=%d nx=%d nyl=%d rows_iter=%d stages=%d cur=%d\n", s.kernel, s.grid, s.block.x, s.block.y, s.dyn_smem,
+            (void *)s.base, 2 * h->lattice_bytes + kFlagBytes, (void *)s.buf[0], (void *)s.buf[1], h->plane, a.pitch,
+            a.mask_pitch, a.nx, a.nyl, a.rows_iter, a.stages, h->cur);
+    for (int k = 0; k < lbm::kSpeeds; ++k) fprintf(stderr, "[lbm]   src[%d]=%p dst[%d]=%p\n", k, (const void *)a.src[k], k, (void *)a.dst[k]);
+    for (int i = 0; i < 3; ++i) fprintf(stderr, "[lbm]   ghost_north[%d]=%p ghost_south[%d]=%p\n", i, (void *)a.ghost_north[i], i, (void *)a.ghost_south[i]);
+    fprintf(stderr, "[lbm]   mask=%p partials=%p tot_u=%p ticket=%p step=%p\n", (const void *)a.mask, (void *)a.partials, (void *)a.tot_u, (void *)a.ticket, (void *)a.step);
+  }
+  switch (s.kernel) {
+    case KERNEL_TMA:
+      if (h->multi) lbm::sweep_tma_kernel<true><<<s.grid, s.block, s.dyn_smem, s.stream>>>(a, s.tmap[h->cur][0], s.tmap[h->cur][1]);
+      else lbm::sweep_tma_kernel<false><<<s.grid, s.block, s.dyn_smem, s.stream>>>(a, s.tmap[h->cur][0], s.tmap[h->cur][1]);
+      break;
+    case KERNEL_LDG4:
+      if (h->multi) lbm::sweep_kernel<4, true><<<s.grid, s.block, 0, s.stream>>>(a);
+      else lbm::sweep_kernel<4, false><<<s.grid, s.block, 0, s.stream>>>(a);
+      break;
+    default:
+      if (h->multi) lbm::sweep_kernel<1, true><<<s.grid, s.block, 0, s.stream>>>(a);
+      else lbm::sweep_kernel<1, false><<<s.grid, s.block, 0, s.stream>>>(a);
   }
   ++h->launches;
-  CUDA_TRY(cudaGetLastError());
+  KERNEL_CHECK(s.stream, "sweep");
   return LBM_OK;
 }
 
@@ -300,14 +400,6 @@ int reset_counters(lbm_handle *h) {
   }
   h->cur = 0;
   h->steps_done = 0;
-  return LBM_OK;
-}
-
-int sync_all(lbm_handle *h) {
-  for (Slab &s : h->slabs) {
-    CUDA_TRY(cudaSetDevice(s.device));
-    CUDA_TRY(cudaStreamSynchronize(s.stream));
-  }
   return LBM_OK;
 }
 
@@ -534,10 +626,10 @@ int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles) 
       const int rows = std::min(rows_per_chunk, s.nyl - r);
       const size_t bytes = (size_t)rows * nx * lbm::kSpeeds * sizeof(float);
       CUDA_TRY(cudaMemcpyAsync(s.stage, cells + (size_t)r * nx * lbm::kSpeeds, bytes, cudaMemcpyHostToDevice, s.stream));
-      lbm::aos_to_soa_kernel<<<rows * chunks_x, lbm::kBlockThreads, 0, s.stream>>>(s.stage, s.buf[0], h->plane,
+      lbm::aos_to_soa_kernel<<<rows * chunks_x, lbm::kBlockThreads, 0, s.stream>>>(s.stage, s.buf[0] + lbm::kCol0, h->plane,
                                                                                  h->pitch, nx, rows, 1 + r);
       ++h->launches;
-      CUDA_TRY(cudaGetLastError());
+      KERNEL_CHECK(s.stream, "aos_to_soa");
       // the staging buffer is reused: wait for the transposition before the next copy lands (a pageable
       // source makes the copy synchronous anyway)
       CUDA_TRY(cudaStreamSynchronize(s.stream));
@@ -550,10 +642,10 @@ int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles) 
       const int rows = std::min(rows_per_mchunk, s.nyl - r);
       CUDA_TRY(cudaMemcpyAsync(stage8, obst + (size_t)r * nx, (size_t)rows * nx, cudaMemcpyHostToDevice, s.stream));
       const long long threads = (long long)rows * words * 32;
-      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(stage8, s.mask, h->pitch, nx,
+      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(stage8, s.mask, h->mask_pitch, nx,
                                                                                   rows, 1 + r, s.free_dev);
       ++h->launches;
-      CUDA_TRY(cudaGetLastError());
+      KERNEL_CHECK(s.stream, "pack_mask");
       CUDA_TRY(cudaStreamSynchronize(s.stream));
     }
   }
@@ -575,9 +667,9 @@ int lbm_init_synthetic(lbm_handle *h, uint64_t seed, float solid_prob) {
     const int words = (h->nx + 31) / 32;
     const long long threads = (long long)s.nyl * words * 32;
     lbm::synthetic_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
-        s.mask, h->pitch, h->nx, h->ny, s.row0, s.nyl, seed, threshold24, s.free_dev);
+        s.mask, h->mask_pitch, h->nx, h->ny, s.row0, s.nyl, seed, threshold24, s.free_dev);
     h->launches += 2;
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK(s.stream, "fill_planes/synthetic_mask");
   }
   return finish_upload(h);
 }
@@ -601,22 +693,23 @@ int lbm_run(lbm_handle *h, int iters) {
       if (arow < s.row0 || arow >= s.row0 + s.nyl) continue;
       CUDA_TRY(cudaSetDevice(s.device));
       lbm::accelerate_flow_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
-          s.buf[h->cur], h->plane, h->pitch, h->nx, arow - s.row0 + 1, s.mask, w1, w2);
+          s.buf[h->cur] + lbm::kCol0, h->plane, h->pitch, h->nx, arow - s.row0 + 1, s.mask, h->mask_pitch, w1, w2);
       ++h->launches;
-      CUDA_TRY(cudaGetLastError());
+      KERNEL_CHECK(s.stream, "accelerate_flow");
     }
     // ... then the initial halo: every slab fills its neighbours' ghost rows and publishes epoch 1
     for (Slab &s : h->slabs) {
       CUDA_TRY(cudaSetDevice(s.device));
-      lbm::push_halo_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
-          s.buf[h->cur], s.north_buf[h->cur], s.south_buf[h->cur], h->plane, h->pitch, h->nx, s.nyl,
-          s.south_ghost_row);
+      const int n = std::max(h->nx, s.nyl);
+      lbm::init_halo_kernel<<<(n + 255) / 256, 256, 0, s.stream>>>(
+          s.buf[h->cur] + lbm::kCol0, s.north_buf[h->cur] + lbm::kCol0, s.south_buf[h->cur] + lbm::kCol0, h->plane,
+          h->pitch, h->nx, s.nyl, s.south_ghost_row);
       ++h->launches;
       if (h->multi) {
         lbm::publish_epoch_kernel<<<1, 1, 0, s.stream>>>(s.flag_to_south, s.flag_to_north, 1);
         ++h->launches;
       }
-      CUDA_TRY(cudaGetLastError());
+      KERNEL_CHECK(s.stream, "init_halo/publish_epoch");
     }
     h->first_run_pending = false;
   }
@@ -692,10 +785,10 @@ int lbm_download(lbm_handle *h, float *cells_aos, float *av_vels) {
       for (int r = 0; r < s.nyl; r += rows_per_chunk) {
         const int rows = std::min(rows_per_chunk, s.nyl - r);
         const size_t bytes = (size_t)rows * nx * lbm::kSpeeds * sizeof(float);
-        lbm::soa_to_aos_kernel<<<rows * chunks_x, lbm::kBlockThreads, 0, s.stream>>>(s.buf[h->cur], s.stage, h->plane,
+        lbm::soa_to_aos_kernel<<<rows * chunks_x, lbm::kBlockThreads, 0, s.stream>>>(s.buf[h->cur] + lbm::kCol0, s.stage, h->plane,
                                                                                    h->pitch, nx, rows, 1 + r);
         ++h->launches;
-        CUDA_TRY(cudaGetLastError());
+        KERNEL_CHECK(s.stream, "soa_to_aos");
         CUDA_TRY(cudaMemcpyAsync(cells + (size_t)r * nx * lbm::kSpeeds, s.stage, bytes, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaStreamSynchronize(s.stream));
       }
@@ -733,7 +826,11 @@ int lbm_launch_count(lbm_handle *h, long long *count) {
 }
 const char *lbm_kernel_variant(lbm_handle *h) {
   if (!h || h->slabs.empty()) return "";
-  return h->slabs[0].vec == 4 ? "vec4" : "scalar";
+  switch (h->slabs[0].kernel) {
+    case KERNEL_TMA: return "tma";
+    case KERNEL_LDG4: return "vec4";
+    default: return "scalar";
+  }
 }
 int lbm_rows(lbm_handle *h, int *row_begin, int *row_count) {
   if (!h || !row_begin || !row_count) return fail(LBM_E_ARG, "null argument");
@@ -744,6 +841,24 @@ int lbm_rows(lbm_handle *h, int *row_begin, int *row_count) {
     *row_begin = 0;
     *row_count = h->ny;
   }
+  return LBM_OK;
+}
+
+int lbm_selftest_math(int device, unsigned long long pairs, unsigned long long *counts) {
+  if (!counts) return fail(LBM_E_ARG, "null argument");
+  int ndev = 0;
+  int rc = lbm_device_count(&ndev);
+  if (rc) return rc;
+  if (device < 0 || device >= ndev) return fail(LBM_E_ARG, "GPU %d not visible (%d devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  unsigned long long *d = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d, 7 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(d, 0, 7 * sizeof(unsigned long long)));
+  lbm::selftest_math_kernel<<<148 * 8, 256>>>(d, pairs, 0x5EEDull);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(counts, d, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(LBM_E_CUDA, "math self-test failed: %s", cudaGetErrorString(e));
   return LBM_OK;
 }
 

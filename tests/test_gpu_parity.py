@@ -45,7 +45,7 @@ def test_shipped_inputs_bit_exact_short(oracle, lbm, case):
     obst = lbm.load_obstacles(p.nx, p.ny, obstacles_path(case))
     assert np.array_equal(obst, oracle.load_obstacles(obstacles_path(case), p.nx, p.ny))
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == "vec4"
+        assert s.kernel_variant == "tma"
     _assert_matches_oracle(oracle, lbm, p, op, lbm.initial_cells(p), obst, 1500)
 
 
@@ -60,9 +60,32 @@ def test_scalar_kernel_ragged_sizes(oracle, lbm, nx, ny):
 
 @pytest.mark.parametrize("nx,ny", [(128, 1), (128, 2), (256, 7), (1024, 33), (2048, 16), (384, 9)])
 def test_vec4_kernel_random(oracle, lbm, nx, ny):
-    """float4 path with random solids everywhere (also on the driven row) and a perturbed lattice."""
+    """TMA path (nx % 128 == 0) with random solids everywhere (also on the driven row) and a perturbed
+    lattice; 128-wide and 256-wide units, partial last row-tiles."""
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 30, seed=nx + ny, solid_frac=0.1)
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30)
+
+
+@pytest.mark.parametrize("nx,ny", [(128, 3), (256, 64), (1024, 9), (384, 20)])
+def test_ldg_float4_kernel_random(oracle, lbm, nx, ny, monkeypatch):
+    """The register-path float4 kernel (kept beside the TMA kernel as the measured alternative)."""
+    monkeypatch.setenv("LBM_B200_KERNEL", "ldg")
+    p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 30, seed=nx * 7 + ny, solid_frac=0.1)
+    with lbm.Solver(p) as s:
+        assert s.kernel_variant == "vec4"
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30)
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30, devices=[0, 0])
+
+
+@pytest.mark.parametrize("stages", [2, 4, 6])
+def test_tma_pipeline_depths(oracle, lbm, stages, monkeypatch):
+    """Every supported TMA pipeline depth gives the same lattice (more units than stages per CTA)."""
+    monkeypatch.setenv("LBM_B200_STAGES", str(stages))
+    monkeypatch.setenv("LBM_B200_BLOCKS_PER_SM", "1")
+    p, op, cells, obst = _random_problem(oracle, lbm, 512, 2500, 6, seed=stages, solid_frac=0.02)
+    with lbm.Solver(p) as s:
+        assert s.kernel_variant == "tma"
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 6)
 
 
 def test_run_in_pieces_equals_one_run(oracle, lbm):
@@ -110,6 +133,15 @@ def test_synthetic_channel_matches_host_twin(oracle, lbm):
         got_cells, got_av = s.download()
     assert np.array_equal(got_cells.view(np.uint32), want_cells.view(np.uint32))
     assert ulp_distance(got_av, want_av).max() <= 1
+
+
+def test_division_and_sqrt_helpers_match_ieee_library(lbm):
+    """The kernels replace __fdiv_rn/__fsqrt_rn by the library's own fast-path sequence under a wider
+    guard (zero numerators, sqrt(0)).  Exhaustive for rho/9, rho/36 and sqrt; 2^30 random pairs for a/b."""
+    r = lbm.selftest_math(0, 1 << 30)
+    assert r["div9_n"] == (0x5D800000 - 0x21800000 + 1)
+    assert r["sqrt_n"] > 1.9e9 and r["div_n"] > 0.9 * (1 << 30)
+    assert r["div9_bad"] == 0 and r["div36_bad"] == 0 and r["sqrt_bad"] == 0 and r["div_bad"] == 0
 
 
 def test_errors_are_reported_not_thrown(lbm):
