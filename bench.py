@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--workload", choices=["channel16384", "weak32768"], default="channel16384")
     ap.add_argument("--nx", type=int, default=0, help="override the grid width (development only)")
     ap.add_argument("--ny", type=int, default=0, help="override the grid height (development only)")
+    ap.add_argument("--local-slabs", type=int, default=1,
+                    help="development only: cut the grid into this many row slabs that all live on GPU 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU time budget of the cpu_baseline sample")
@@ -210,6 +212,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
 
     lbm = importlib.import_module("lbm-graphcore_b200")  # raises if liblbm_b200.so is missing: no fallback
+    slabs = importlib.import_module("lbm-graphcore_b200.slabs")
     if lbm.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device visible; the solver has no CPU path")
 
@@ -237,13 +240,10 @@ def main():
     p = lbm.Params(nx, ny, W + K, REYNOLDS_DIM, DENSITY, ACCEL, OMEGA)
 
     if world == 1:
-        solver = lbm.Solver(p, num_gpus=1)
+        solver = lbm.Solver(p, devices=[0] * args.local_slabs) if args.local_slabs > 1 else lbm.Solver(p, num_gpus=1)
     else:
         solver = lbm.Solver(p, rank=rank, world=world, device=local_rank)
-        blobs = [None] * world
-        dist.all_gather_object(blobs, solver.ipc_export())
-        solver.ipc_connect(b"".join(blobs))
-        barrier()
+        slabs.connect_ring(solver, dist)  # CUDA-IPC handles all-gathered, ring neighbours mapped
 
     # ---- device-resident timing ----------------------------------------------------------------
     solver.init_synthetic(SEED, SOLID_PROB)
@@ -262,17 +262,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = solver.launch_count - launches0
     barrier()
-    tot = solver.download_tot_u()
-    free_local = solver.free_cells
-    if dist is not None:
-        import torch
-        allt = [None] * world
-        dist.all_gather_object(allt, (tot, free_local))
-        tot = np.sum([a for a, _ in allt], axis=0)  # rank order
-        free_total = sum(f for _, f in allt)
-    else:
-        free_total = free_local
-    av_last = float(np.float32(tot[-1]) / np.float32(free_total))
+    av_last = float(slabs.combine_av_vels(dist, solver.download_tot_u(), solver.free_cells)[-1])  # rank order
     if not np.isfinite(av_last):
         raise SystemExit("bench.py: av_vels is not finite")
     cells = nx * ny
@@ -283,8 +273,7 @@ def main():
     # ---- end-to-end through host buffers -------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        rows0 = rank * ny // world
-        rows = (rank + 1) * ny // world - rows0
+        rows0, rows = slabs.slab_rows(rank, world, ny)
         p2 = lbm.Params(nx, ny, K, REYNOLDS_DIM, DENSITY, ACCEL, OMEGA)
         nbytes_cells = rows * nx * 9 * 4
         nbytes_obst = rows * nx
@@ -305,9 +294,7 @@ def main():
             s2 = lbm.Solver(p2, num_gpus=1)
         else:
             s2 = lbm.Solver(p2, rank=rank, world=world, device=local_rank)
-            blobs = [None] * world
-            dist.all_gather_object(blobs, s2.ipc_export())
-            s2.ipc_connect(b"".join(blobs))
+            slabs.connect_ring(s2, dist)
         barrier()
         t0 = time.perf_counter()
         s2.upload_raw(hc, ho)

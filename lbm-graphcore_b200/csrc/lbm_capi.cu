@@ -115,6 +115,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+int env_int(const char *name, int fallback) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : fallback;
+}
+
 int encode_lattice_map(lbm_handle *h, float *buf, int box_w, int box_h, CUtensorMap *out) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
@@ -128,8 +133,11 @@ int encode_lattice_map(lbm_handle *h, float *buf, int box_w, int box_h, CUtensor
   const cuuint64_t strides[2] = {(cuuint64_t)h->pitch * sizeof(float), (cuuint64_t)h->plane * sizeof(float)};
   const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
+  static const CUtensorMapL2promotion promos[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
+  const int promo = std::max(0, std::min(3, env_int("LBM_B200_L2PROMO", 3)));
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promos[promo],
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LBM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return LBM_OK;
@@ -151,11 +159,6 @@ template <typename K>
 int occupancy_blocks(K kernel, size_t dyn_smem, int *out) {
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, lbm::kBlockThreads, dyn_smem));
   return LBM_OK;
-}
-
-int env_int(const char *name, int fallback) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : fallback;
 }
 
 // Choose the sweep kernel and its launch shape for one slab.  Called after alloc_slab.

@@ -1,0 +1,67 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped on a 1-GPU box): row slabs on different B200s whose sweep
+kernels store their halo rows straight into each other's memory over NVLink.  The lattice must be
+bit-identical to the single-domain CPU oracle whatever the decomposition."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, ulp_distance
+from rank_worker import problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpus(lbm, n):
+    have = lbm.device_count()
+    if have < n:
+        pytest.skip(f"needs {n} GPUs, {have} visible")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("nx,ny,gpus", [(256, 64, 2), (100, 19, 2), (1024, 33, 2), (256, 96, 4), (384, 50, 8)])
+def test_in_process_multi_gpu_bit_exact(oracle, lbm, nx, ny, gpus):
+    """lbm_create(num_gpus = N): one process drives N GPUs (the reference's -n flag, main/LbmRunner.cpp:19)."""
+    _need_gpus(lbm, gpus)
+    iters = 40
+    p, cells, obst = problem(lbm, nx, ny, iters, seed=nx + ny + gpus)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    with lbm.Solver(p, num_gpus=gpus) as s:
+        s.upload(cells, obst)
+        s.run(iters)
+        got_cells, got_av = s.download()
+    assert np.array_equal(got_cells.view(np.uint32), want_cells.view(np.uint32))
+    assert ulp_distance(got_av, want_av).max() <= 1
+
+
+@pytest.mark.parametrize("nx,ny,world,pieces", [(256, 64, 2, 1), (130, 21, 2, 3), (2048, 512, 2, 1), (512, 100, 4, 2)])
+def test_one_process_per_gpu_bit_exact(oracle, lbm, tmp_path, nx, ny, world, pieces):
+    """torchrun, one rank per GPU, CUDA-IPC mapped neighbours (how bench.py --gpus N runs)."""
+    _need_gpus(lbm, world)
+    iters, seed = 30, 11
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "rank_worker.py"), str(tmp_path), str(nx), str(ny), str(iters), str(seed),
+           str(pieces)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    p, cells, obst = problem(lbm, nx, ny, iters, seed)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    rows = 0
+    for rank in range(world):
+        z = np.load(tmp_path / f"rank{rank}.npz")
+        r0, got = int(z["row_begin"]), z["cells"]
+        assert np.array_equal(got.view(np.uint32), want_cells[r0:r0 + got.shape[0]].view(np.uint32)), f"rank {rank}"
+        assert ulp_distance(z["av_vels"], want_av).max() <= 1
+        rows += got.shape[0]
+    assert rows == ny
