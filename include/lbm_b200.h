@@ -95,8 +95,8 @@ int lbm_steps_done(lbm_handle *h, int *steps);
 int lbm_free_cells(lbm_handle *h, long long *count);
 /* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int lbm_launch_count(lbm_handle *h, long long *count);
-/* name of the sweep kernel variant in use: "tma" (nx % 128 == 0), "scalar" (any nx), or "vec4" (the
- * register-path float4 kernel, selectable with LBM_B200_KERNEL=ldg for comparison runs) */
+/* name of the sweep kernel variant in use: "vec4" (nx % 128 == 0: 128-bit loads and stores) or "scalar"
+ * (any nx; LBM_B200_KERNEL=scalar forces it for comparison runs) */
 const char *lbm_kernel_variant(lbm_handle *h);
 
 /* ------------------------------------------------------------------------------------------------

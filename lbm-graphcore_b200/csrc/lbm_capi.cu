@@ -36,7 +36,7 @@ int fail(int code, const char *fmt, ...) {
       return fail(LBM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-enum { KERNEL_SCALAR = 0, KERNEL_LDG4 = 1, KERNEL_TMA = 2 };
+enum { KERNEL_SCALAR = 0, KERNEL_VEC4 = 1 };
 // LBM_B200_DEBUG_SYNC=1: synchronise after every kernel launch and name the kernel that failed
 #define KERNEL_CHECK(stream, name)                                                                      \
   do {                                                                                                   \
@@ -60,9 +60,10 @@ struct Slab {
   int *flags = nullptr;  // [0] from_south, [1] from_north
   // private allocations
   uint32_t *mask = nullptr;
-  double *partials = nullptr;
+  double *partials = nullptr;      // [grid] CTA partials
+  double *row_partials = nullptr;  // [tiles_y]
   double *tot_u = nullptr;
-  unsigned *ticket = nullptr;  // [0] grid ticket, [1..2] edge tickets
+  unsigned *ticket = nullptr;      // [0] tile-row ticket, [1..2] edge tickets, [4 ..] per-tile-row CTA tickets
   int *step = nullptr;         // [0] step, [1] error
   unsigned long long *free_dev = nullptr;
   float *stage = nullptr;
@@ -73,13 +74,9 @@ struct Slab {
   int *flag_to_north = nullptr;
   int south_ghost_row = 0;
   // launch configuration
-  int kernel = 0;  // KERNEL_SCALAR / KERNEL_LDG4 / KERNEL_TMA
-  dim3 block;
-  int grid = 1;
-  int rows_iter = 1;   // LDG kernels: rows each thread walks per tile
-  int stages = 0;      // TMA kernel: pipeline depth
-  size_t dyn_smem = 0; // TMA kernel: bytes of dynamic shared memory
-  CUtensorMap tmap[2][2]; // TMA kernel: 3-D maps (x, row, plane) per lattice buffer: [buffer][narrow|wide box]
+  int kernel = 0;  // KERNEL_SCALAR / KERNEL_VEC4
+  int tiles_y = 1; // tile rows this slab sweeps = ceil((nyl + 2) / 8)
+  int grid = 1;    // one CTA per tile
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long free_cells = 0;
 };
@@ -89,8 +86,10 @@ struct Slab {
 struct lbm_handle {
   int nx = 0, ny = 0, max_iters = 0;
   float density = 0, accel = 0, omega = 0;
-  int pitch = 0, mask_pitch = 0, rows_alloc = 0;
-  size_t plane = 0;  // floats
+  int ntx = 0;        // tiles per storage row
+  int tiles_y = 0;    // tile rows allocated per slab (same on every slab so IPC offsets agree)
+  int rows_alloc = 0; // storage rows per slab incl. the two ghost rows
+  size_t lattice_floats = 0;
   size_t lattice_bytes = 0;
   std::vector<Slab> slabs;
   bool multi = false;      // more than one slab in the ring
@@ -110,116 +109,14 @@ namespace {
 
 size_t blob_bytes() { return sizeof(cudaIpcMemHandle_t) + 4 * sizeof(int); }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int env_int(const char *name, int fallback) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : fallback;
-}
-
-int encode_lattice_map(lbm_handle *h, float *buf, int box_w, int box_h, CUtensorMap *out) {
-  static EncodeTiledFn encode = nullptr;
-  if (!encode) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(LBM_E_CUDA, "cuTensorMapEncodeTiled is not available");
-    encode = reinterpret_cast<EncodeTiledFn>(fn);
-  }
-  const cuuint64_t dims[3] = {(cuuint64_t)h->pitch, (cuuint64_t)h->rows_alloc, (cuuint64_t)lbm::kSpeeds};
-  const cuuint64_t strides[2] = {(cuuint64_t)h->pitch * sizeof(float), (cuuint64_t)h->plane * sizeof(float)};
-  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
-  const cuuint32_t estr[3] = {1u, 1u, 1u};
-  static const CUtensorMapL2promotion promos[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
-                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
-  const int promo = std::max(0, std::min(3, env_int("LBM_B200_L2PROMO", 3)));
-  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promos[promo],
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(LBM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return LBM_OK;
-}
-
-int pick_tx(int nx, int vec) {
-  if (vec == 4) {
-    const int lanes = nx / 4;
-    for (int tx = 256; tx >= 32; tx >>= 1)
-      if (tx <= lanes) return tx;
-    return 32;
-  }
-  int tx = 32;
-  while (tx < 256 && tx < nx) tx <<= 1;
-  return tx;
-}
-
-template <typename K>
-int occupancy_blocks(K kernel, size_t dyn_smem, int *out) {
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, lbm::kBlockThreads, dyn_smem));
-  return LBM_OK;
-}
-
-// Choose the sweep kernel and its launch shape for one slab.  Called after alloc_slab.
+// Choose the sweep kernel and its launch shape for one slab: one CTA of 8 warps per 128 x 8 tile.
 int configure_launch(lbm_handle *h, Slab &s) {
-  CUDA_TRY(cudaSetDevice(s.device));
-  int sms = 0, per_sm = 0, rc = LBM_OK;
-  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
-  s.kernel = (h->nx % 128 == 0) ? KERNEL_TMA : KERNEL_SCALAR;
-  // development knob (profiling sweeps): LBM_B200_KERNEL=ldg forces the register-path float4 kernel
+  s.kernel = (h->nx % lbm::kTileW == 0) ? KERNEL_VEC4 : KERNEL_SCALAR;
+  // development knob (parity tests of the scalar path on vectorisable sizes)
   if (const char *e = getenv("LBM_B200_KERNEL"))
-    if (s.kernel == KERNEL_TMA && !strcmp(e, "ldg")) s.kernel = KERNEL_LDG4;
-
-  if (s.kernel == KERNEL_TMA) {
-    s.block = dim3(32, lbm::kUnitH, 1);  // one warp per row of a 128 x 8 unit
-    s.stages = std::max(2, std::min(lbm::kMaxStages, env_int("LBM_B200_STAGES", 4)));
-    s.dyn_smem = (size_t)s.stages * lbm::kStageFloats * sizeof(float);
-    if (h->multi) {
-      CUDA_TRY(cudaFuncSetAttribute(lbm::sweep_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.dyn_smem));
-      rc = occupancy_blocks(lbm::sweep_tma_kernel<true>, s.dyn_smem, &per_sm);
-    } else {
-      CUDA_TRY(cudaFuncSetAttribute(lbm::sweep_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.dyn_smem));
-      rc = occupancy_blocks(lbm::sweep_tma_kernel<false>, s.dyn_smem, &per_sm);
-    }
-    if (rc) return rc;
-    for (int b = 0; b < 2; ++b) {
-      rc = encode_lattice_map(h, s.buf[b], lbm::kUnitW, lbm::kUnitH, &s.tmap[b][0]);
-      if (!rc) rc = encode_lattice_map(h, s.buf[b], lbm::kWideW, lbm::kUnitH, &s.tmap[b][1]);
-      if (rc) return rc;
-    }
-    // one CTA per SM: measured faster than two (profiles/): a second CTA adds no bandwidth (the copies are
-    // already `stages` deep) but its extra in-flight boxes push the shared edge sectors of neighbouring
-    // units out of L2 (+13 % DRAM reads)
-    per_sm = std::max(1, std::min(per_sm, env_int("LBM_B200_BLOCKS_PER_SM", 1)));
-    const long long units = (long long)(h->nx / lbm::kUnitW) * ((s.nyl + lbm::kUnitH - 1) / lbm::kUnitH);
-    s.grid = (int)std::max<long long>(1, std::min<long long>({units, (long long)sms * per_sm, (long long)lbm::kMaxPartials}));
-    return LBM_OK;
-  }
-
-  const int vec = s.kernel == KERNEL_LDG4 ? 4 : 1;
-  const int tx = pick_tx(h->nx, vec);
-  s.block = dim3(tx, lbm::kBlockThreads / tx, 1);
-  if (vec == 4) rc = h->multi ? occupancy_blocks(lbm::sweep_kernel<4, true>, 0, &per_sm) : occupancy_blocks(lbm::sweep_kernel<4, false>, 0, &per_sm);
-  else rc = h->multi ? occupancy_blocks(lbm::sweep_kernel<1, true>, 0, &per_sm) : occupancy_blocks(lbm::sweep_kernel<1, false>, 0, &per_sm);
-  if (rc) return rc;
-  per_sm = std::max(1, std::min(per_sm, env_int("LBM_B200_BLOCKS_PER_SM", per_sm)));
-  const long long resident = std::min<long long>((long long)sms * per_sm, lbm::kMaxPartials);
-  // tile height: as many rows per thread as still leaves >= 64 tiles per resident block (tail balance)
-  const int tile_w = tx * vec;
-  const long long tiles_x = (h->nx + tile_w - 1) / tile_w;
-  long long ntiles = 0;
-  for (s.rows_iter = 16; s.rows_iter >= 1; s.rows_iter >>= 1) {
-    const int tile_h = (int)s.block.y * s.rows_iter;
-    ntiles = tiles_x * ((s.nyl + tile_h - 1) / tile_h);
-    if (ntiles >= 64 * resident || s.rows_iter == 1) break;
-  }
-  if (const char *e = getenv("LBM_B200_ROWS_ITER")) {
-    s.rows_iter = std::max(1, atoi(e));
-    const int tile_h = (int)s.block.y * s.rows_iter;
-    ntiles = tiles_x * ((s.nyl + tile_h - 1) / tile_h);
-  }
-  s.grid = (int)std::max<long long>(std::min<long long>(ntiles, resident), 1);
+    if (!strcmp(e, "scalar")) s.kernel = KERNEL_SCALAR;
+  s.tiles_y = (s.nyl + 2 + lbm::kTileH - 1) / lbm::kTileH;
+  s.grid = h->ntx * s.tiles_y;
   return LBM_OK;
 }
 
@@ -234,14 +131,15 @@ int alloc_slab(lbm_handle *h, Slab &s) {
   s.buf[1] = reinterpret_cast<float *>(s.base + h->lattice_bytes);
   s.flags = reinterpret_cast<int *>(s.base + 2 * h->lattice_bytes);
   CUDA_TRY(cudaMemset(s.flags, 0, kFlagBytes));
-  const size_t mask_bytes = (size_t)h->rows_alloc * h->mask_pitch * sizeof(uint32_t);
+  const size_t mask_bytes = (size_t)h->tiles_y * h->ntx * lbm::kTileMaskWords * sizeof(uint32_t);
   CUDA_TRY(cudaMalloc((void **)&s.mask, mask_bytes));
   CUDA_TRY(cudaMemset(s.mask, 0, mask_bytes));
-  CUDA_TRY(cudaMalloc((void **)&s.partials, lbm::kMaxPartials * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s.partials, (size_t)h->tiles_y * h->ntx * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s.row_partials, (size_t)h->tiles_y * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s.tot_u, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
   CUDA_TRY(cudaMemset(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&s.ticket, 4 * sizeof(unsigned)));
-  CUDA_TRY(cudaMemset(s.ticket, 0, 4 * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc((void **)&s.ticket, (size_t)(4 + h->tiles_y) * sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(s.ticket, 0, (size_t)(4 + h->tiles_y) * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc((void **)&s.step, 2 * sizeof(int)));
   CUDA_TRY(cudaMemset(s.step, 0, 2 * sizeof(int)));
   CUDA_TRY(cudaMalloc((void **)&s.free_dev, sizeof(unsigned long long)));
@@ -260,6 +158,7 @@ void free_slab(Slab &s) {
   cudaFree(s.step);
   cudaFree(s.ticket);
   cudaFree(s.tot_u);
+  cudaFree(s.row_partials);
   cudaFree(s.partials);
   cudaFree(s.mask);
   cudaFree(s.base);
@@ -271,8 +170,8 @@ int check_problem(int nx, int ny, int max_iters, int slabs) {
   if (max_iters < 0) return fail(LBM_E_ARG, "max_iters must be >= 0 (got %d)", max_iters);
   if (slabs < 1) return fail(LBM_E_ARG, "need at least one GPU/slab (got %d)", slabs);
   if (ny < slabs) return fail(LBM_E_ARG, "cannot cut %d rows into %d slabs", ny, slabs);
-  if ((long long)(ny / slabs + 4) * ((nx + lbm::kCol0 + 1 + 31) / 32 * 32) >= (1ll << 31))
-    return fail(LBM_E_ARG, "slab of %dx%d cells exceeds 2^31 cells per plane", nx, ny / slabs + 1);
+  const long long tiles = (long long)((nx + lbm::kTileW - 1) / lbm::kTileW) * ((ny / slabs + 3 + lbm::kTileH) / lbm::kTileH);
+  if (tiles >= (1ll << 31)) return fail(LBM_E_ARG, "slab of %dx%d cells exceeds 2^31 tiles", nx, ny / slabs + 1);
   return LBM_OK;
 }
 
@@ -280,78 +179,57 @@ void set_geometry(lbm_handle *h, int nx, int ny, int max_iters, float density, f
                   int ring) {
   h->nx = nx; h->ny = ny; h->max_iters = max_iters;
   h->density = density; h->accel = accel; h->omega = omega;
-  h->pitch = (nx + lbm::kCol0 + 1 + 31) / 32 * 32;  // [32 ghost/pad | nx cells | east ghost | pad]
-  h->mask_pitch = (nx + 31) / 32;
-  h->rows_alloc = (ny + ring - 1) / ring + 2;  // same on every slab so plane strides agree
-  h->plane = (size_t)h->rows_alloc * h->pitch;
-  h->lattice_bytes = h->plane * lbm::kSpeeds * sizeof(float);
+  h->ntx = (nx + lbm::kTileW - 1) / lbm::kTileW;
+  h->rows_alloc = (ny + ring - 1) / ring + 2;  // the tallest slab + two ghost rows; same on every slab
+  h->tiles_y = (h->rows_alloc + lbm::kTileH - 1) / lbm::kTileH;
+  h->lattice_floats = (size_t)h->tiles_y * h->ntx * lbm::kTileFloats;
+  h->lattice_bytes = h->lattice_floats * sizeof(float);
   h->multi = ring > 1;
 }
-
-// pointer to (storage row 0, column kCol0) of plane k of a lattice buffer
-inline float *plane_ptr(const lbm_handle *h, float *buf, int k) { return buf + (size_t)k * h->plane + lbm::kCol0; }
 
 lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   lbm::SweepArgs a{};
   const int c = h->cur;
-  static const int north_planes[3] = {2, 5, 6}, south_planes[3] = {4, 7, 8};
-  for (int k = 0; k < lbm::kSpeeds; ++k) {
-    a.src[k] = plane_ptr(h, s.buf[c], k);
-    a.dst[k] = plane_ptr(h, s.buf[c ^ 1], k);
-  }
-  for (int i = 0; i < 3; ++i) {
-    a.ghost_north[i] = plane_ptr(h, s.north_buf[c ^ 1], north_planes[i]);  // storage row 0
-    a.ghost_south[i] = plane_ptr(h, s.south_buf[c ^ 1], south_planes[i]) + (size_t)s.south_ghost_row * h->pitch;
-  }
+  a.src = s.buf[c];
+  a.dst = s.buf[c ^ 1];
+  a.north_dst = s.north_buf[c ^ 1];
+  a.south_dst = s.south_buf[c ^ 1];
   a.mask = s.mask;
-  a.mask_pitch = h->mask_pitch;
-  a.pitch = h->pitch;
+  a.ntx = h->ntx;
+  a.tiles_y = s.tiles_y;
   a.nx = h->nx;
   a.nyl = s.nyl;
+  a.south_ghost_row = s.south_ghost_row;
   const int arow = h->ny - 2;  // main/LastChance.cpp:198 (never matches when ny < 2, like the reference)
   a.accel_row = (arow >= s.row0 && arow < s.row0 + s.nyl) ? (arow - s.row0 + 1) : -1;
-  a.rows_iter = s.rows_iter;
-  a.stages = s.stages;
   a.omega = h->omega;
   a.one_minus_omega = 1 - h->omega;                 // main/LastChance.cpp:387
   a.w1 = h->density * h->accel / 9.f;               // main/LastChance.cpp:158
   a.w2 = h->density * h->accel / 36.f;              // :159
   a.partials = s.partials;
+  a.row_partials = s.row_partials;
   a.tot_u = s.tot_u;
   a.ticket = s.ticket;
+  a.edge_ticket = s.ticket + 1;
+  a.row_ticket = s.ticket + 4;
   a.step = s.step;
   a.flag_from_south = s.flags + 0;
   a.flag_from_north = s.flags + 1;
   a.flag_to_south = s.flag_to_south;
   a.flag_to_north = s.flag_to_north;
-  a.edge_ticket = s.ticket + 1;
   a.error = s.step + 1;
   return a;
 }
 
 int launch_sweep(lbm_handle *h, Slab &s) {
   const lbm::SweepArgs a = sweep_args(h, s);
-  if (getenv("LBM_B200_DEBUG_ARGS")) {
-    fprintf(stderr, "[lbm] sweep kernel=%d grid=%d block=(%u,%u) smem=%zu base=%p bytes=%zu buf0=%p buf1=%p plane=%zu pitch=%d "
-            "mask_pitch=%d nx=%d nyl=%d rows_iter=%d stages=%d cur=%d\n", s.kernel, s.grid, s.block.x, s.block.y, s.dyn_smem,
-            (void *)s.base, 2 * h->lattice_bytes + kFlagBytes, (void *)s.buf[0], (void *)s.buf[1], h->plane, a.pitch,
-            a.mask_pitch, a.nx, a.nyl, a.rows_iter, a.stages, h->cur);
-    for (int k = 0; k < lbm::kSpeeds; ++k) fprintf(stderr, "[lbm]   src[%d]=%p dst[%d]=%p\n", k, (const void *)a.src[k], k, (void *)a.dst[k]);
-    for (int i = 0; i < 3; ++i) fprintf(stderr, "[lbm]   ghost_north[%d]=%p ghost_south[%d]=%p\n", i, (void *)a.ghost_north[i], i, (void *)a.ghost_south[i]);
-    fprintf(stderr, "[lbm]   mask=%p partials=%p tot_u=%p ticket=%p step=%p\n", (const void *)a.mask, (void *)a.partials, (void *)a.tot_u, (void *)a.ticket, (void *)a.step);
-  }
-  switch (s.kernel) {
-    case KERNEL_TMA:
-      if (h->multi) lbm::sweep_tma_kernel<true><<<s.grid, s.block, s.dyn_smem, s.stream>>>(a, s.tmap[h->cur][0], s.tmap[h->cur][1]);
-      else lbm::sweep_tma_kernel<false><<<s.grid, s.block, s.dyn_smem, s.stream>>>(a, s.tmap[h->cur][0], s.tmap[h->cur][1]);
-      break;
-    case KERNEL_LDG4:
-      if (h->multi) lbm::sweep_kernel<4, true><<<s.grid, s.block, 0, s.stream>>>(a);
-      else lbm::sweep_kernel<4, false><<<s.grid, s.block, 0, s.stream>>>(a);
-      break;
-    default:
-      if (h->multi) lbm::sweep_kernel<1, true><<<s.grid, s.block, 0, s.stream>>>(a);
-      else lbm::sweep_kernel<1, false><<<s.grid, s.block, 0, s.stream>>>(a);
+  const dim3 block(32, lbm::kTileH, 1);
+  if (s.kernel == KERNEL_VEC4) {
+    if (h->multi) lbm::sweep_kernel<true, true><<<s.grid, block, 0, s.stream>>>(a);
+    else lbm::sweep_kernel<true, false><<<s.grid, block, 0, s.stream>>>(a);
+  } else {
+    if (h->multi) lbm::sweep_kernel<false, true><<<s.grid, block, 0, s.stream>>>(a);
+    else lbm::sweep_kernel<false, false><<<s.grid, block, 0, s.stream>>>(a);
   }
   ++h->launches;
   KERNEL_CHECK(s.stream, "sweep");
@@ -396,7 +274,7 @@ int reset_counters(lbm_handle *h) {
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     CUDA_TRY(cudaMemsetAsync(s.flags, 0, kFlagBytes, s.stream));
-    CUDA_TRY(cudaMemsetAsync(s.ticket, 0, 4 * sizeof(unsigned), s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.ticket, 0, (size_t)(4 + h->tiles_y) * sizeof(unsigned), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.step, 0, 2 * sizeof(int), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.free_dev, 0, sizeof(unsigned long long), s.stream));
@@ -550,7 +428,7 @@ int lbm_ipc_export(lbm_handle *h, void *blob) {
   CUDA_TRY(cudaIpcGetMemHandle(&mh, s.base));
   char *p = static_cast<char *>(blob);
   memcpy(p, &mh, sizeof mh);
-  const int meta[4] = {h->rank, s.nyl, h->rows_alloc, h->pitch};
+  const int meta[4] = {h->rank, s.nyl, h->tiles_y, h->ntx};
   memcpy(p + sizeof mh, meta, sizeof meta);
   return LBM_OK;
 }
@@ -573,7 +451,7 @@ int lbm_ipc_connect(lbm_handle *h, const void *blobs) {
     int meta[4];
     memcpy(&mh, b, sizeof mh);
     memcpy(meta, b + sizeof mh, sizeof meta);
-    if (meta[0] != peers[i] || meta[2] != h->rows_alloc || meta[3] != h->pitch)
+    if (meta[0] != peers[i] || meta[2] != h->tiles_y || meta[3] != h->ntx)
       return fail(LBM_E_ARG, "IPC blob %d does not describe rank %d of the same problem", peers[i], peers[i]);
     void *ptr = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
@@ -624,13 +502,11 @@ int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles) 
     const int rows_per_chunk = (int)std::max<size_t>(1, kStageBytes / ((size_t)nx * lbm::kSpeeds * sizeof(float)));
     if ((size_t)nx * lbm::kSpeeds * sizeof(float) > kStageBytes)
       return fail(LBM_E_ARG, "a single row of %d cells does not fit the staging buffer", nx);
-    const int chunks_x = (nx + lbm::kBlockThreads - 1) / lbm::kBlockThreads;
     for (int r = 0; r < s.nyl; r += rows_per_chunk) {
       const int rows = std::min(rows_per_chunk, s.nyl - r);
       const size_t bytes = (size_t)rows * nx * lbm::kSpeeds * sizeof(float);
       CUDA_TRY(cudaMemcpyAsync(s.stage, cells + (size_t)r * nx * lbm::kSpeeds, bytes, cudaMemcpyHostToDevice, s.stream));
-      lbm::aos_to_soa_kernel<<<rows * chunks_x, lbm::kBlockThreads, 0, s.stream>>>(s.stage, s.buf[0] + lbm::kCol0, h->plane,
-                                                                                 h->pitch, nx, rows, 1 + r);
+      lbm::aos_to_tiles_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(s.stage, s.buf[0], h->ntx, nx, rows, 1 + r);
       ++h->launches;
       KERNEL_CHECK(s.stream, "aos_to_soa");
       // the staging buffer is reused: wait for the transposition before the next copy lands (a pageable
@@ -645,8 +521,8 @@ int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles) 
       const int rows = std::min(rows_per_mchunk, s.nyl - r);
       CUDA_TRY(cudaMemcpyAsync(stage8, obst + (size_t)r * nx, (size_t)rows * nx, cudaMemcpyHostToDevice, s.stream));
       const long long threads = (long long)rows * words * 32;
-      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(stage8, s.mask, h->mask_pitch, nx,
-                                                                                  rows, 1 + r, s.free_dev);
+      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(stage8, s.mask, h->ntx, nx, rows, 1 + r,
+                                                                                  s.free_dev);
       ++h->launches;
       KERNEL_CHECK(s.stream, "pack_mask");
       CUDA_TRY(cudaStreamSynchronize(s.stream));
@@ -666,13 +542,13 @@ int lbm_init_synthetic(lbm_handle *h, uint64_t seed, float solid_prob) {
   const float w0 = h->density * 4.f / 9.f, w1 = h->density / 9.f, w2 = h->density / 36.f;
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
-    lbm::fill_planes_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[0], h->plane, w0, w1, w2);
+    lbm::fill_lattice_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[0], h->lattice_floats, w0, w1, w2);
     const int words = (h->nx + 31) / 32;
     const long long threads = (long long)s.nyl * words * 32;
     lbm::synthetic_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
-        s.mask, h->mask_pitch, h->nx, h->ny, s.row0, s.nyl, seed, threshold24, s.free_dev);
+        s.mask, h->ntx, h->nx, h->ny, s.row0, s.nyl, seed, threshold24, s.free_dev);
     h->launches += 2;
-    KERNEL_CHECK(s.stream, "fill_planes/synthetic_mask");
+    KERNEL_CHECK(s.stream, "fill_lattice/synthetic_mask");
   }
   return finish_upload(h);
 }
@@ -695,18 +571,16 @@ int lbm_run(lbm_handle *h, int iters) {
     for (Slab &s : h->slabs) {
       if (arow < s.row0 || arow >= s.row0 + s.nyl) continue;
       CUDA_TRY(cudaSetDevice(s.device));
-      lbm::accelerate_flow_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(
-          s.buf[h->cur] + lbm::kCol0, h->plane, h->pitch, h->nx, arow - s.row0 + 1, s.mask, h->mask_pitch, w1, w2);
+      lbm::accelerate_flow_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(s.buf[h->cur], h->ntx, h->nx, arow - s.row0 + 1,
+                                                                             s.mask, w1, w2);
       ++h->launches;
       KERNEL_CHECK(s.stream, "accelerate_flow");
     }
     // ... then the initial halo: every slab fills its neighbours' ghost rows and publishes epoch 1
     for (Slab &s : h->slabs) {
       CUDA_TRY(cudaSetDevice(s.device));
-      const int n = std::max(h->nx, s.nyl);
-      lbm::init_halo_kernel<<<(n + 255) / 256, 256, 0, s.stream>>>(
-          s.buf[h->cur] + lbm::kCol0, s.north_buf[h->cur] + lbm::kCol0, s.south_buf[h->cur] + lbm::kCol0, h->plane,
-          h->pitch, h->nx, s.nyl, s.south_ghost_row);
+      lbm::init_halo_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(s.buf[h->cur], s.north_buf[h->cur], s.south_buf[h->cur],
+                                                                       h->ntx, h->nx, s.nyl, s.south_ghost_row);
       ++h->launches;
       if (h->multi) {
         lbm::publish_epoch_kernel<<<1, 1, 0, s.stream>>>(s.flag_to_south, s.flag_to_north, 1);
@@ -784,12 +658,10 @@ int lbm_download(lbm_handle *h, float *cells_aos, float *av_vels) {
       const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
       float *cells = cells_aos + first * nx * lbm::kSpeeds;
       const int rows_per_chunk = (int)std::max<size_t>(1, kStageBytes / ((size_t)nx * lbm::kSpeeds * sizeof(float)));
-      const int chunks_x = (nx + lbm::kBlockThreads - 1) / lbm::kBlockThreads;
       for (int r = 0; r < s.nyl; r += rows_per_chunk) {
         const int rows = std::min(rows_per_chunk, s.nyl - r);
         const size_t bytes = (size_t)rows * nx * lbm::kSpeeds * sizeof(float);
-        lbm::soa_to_aos_kernel<<<rows * chunks_x, lbm::kBlockThreads, 0, s.stream>>>(s.buf[h->cur] + lbm::kCol0, s.stage, h->plane,
-                                                                                   h->pitch, nx, rows, 1 + r);
+        lbm::tiles_to_aos_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(s.buf[h->cur], s.stage, h->ntx, nx, rows, 1 + r);
         ++h->launches;
         KERNEL_CHECK(s.stream, "soa_to_aos");
         CUDA_TRY(cudaMemcpyAsync(cells + (size_t)r * nx * lbm::kSpeeds, s.stage, bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -830,8 +702,7 @@ int lbm_launch_count(lbm_handle *h, long long *count) {
 const char *lbm_kernel_variant(lbm_handle *h) {
   if (!h || h->slabs.empty()) return "";
   switch (h->slabs[0].kernel) {
-    case KERNEL_TMA: return "tma";
-    case KERNEL_LDG4: return "vec4";
+    case KERNEL_VEC4: return "vec4";
     default: return "scalar";
   }
 }

@@ -45,47 +45,39 @@ def test_shipped_inputs_bit_exact_short(oracle, lbm, case):
     obst = lbm.load_obstacles(p.nx, p.ny, obstacles_path(case))
     assert np.array_equal(obst, oracle.load_obstacles(obstacles_path(case), p.nx, p.ny))
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == "tma"
+        assert s.kernel_variant == "vec4"
     _assert_matches_oracle(oracle, lbm, p, op, lbm.initial_cells(p), obst, 1500)
 
 
-@pytest.mark.parametrize("nx,ny", [(100, 37), (3, 2), (1, 1), (31, 5), (257, 3), (130, 64)])
+@pytest.mark.parametrize("nx,ny", [(100, 37), (3, 2), (1, 1), (31, 5), (257, 3), (130, 64), (129, 6), (255, 7), (127, 14),
+                                   (385, 15), (2, 8), (1, 23)])
 def test_scalar_kernel_ragged_sizes(oracle, lbm, nx, ny):
-    """Sizes the float4 path cannot take (nx % 128 != 0), including the reference KAT shape 3x2 and 1x1."""
+    """Sizes the float4 path cannot take (nx % 128 != 0), including the reference KAT shape 3x2 and 1x1; last
+    tile columns with 1, 2 and 127 cells; slab heights that put the north ghost row in a tile of its own."""
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 40, seed=nx * 1000 + ny)
     with lbm.Solver(p) as s:
         assert s.kernel_variant == "scalar"
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 40)
 
 
-@pytest.mark.parametrize("nx,ny", [(128, 1), (128, 2), (256, 7), (1024, 33), (2048, 16), (384, 9)])
+@pytest.mark.parametrize("nx,ny", [(128, 1), (128, 2), (256, 7), (1024, 33), (2048, 16), (384, 9), (128, 6), (256, 14),
+                                   (128, 15), (512, 2500)])
 def test_vec4_kernel_random(oracle, lbm, nx, ny):
-    """TMA path (nx % 128 == 0) with random solids everywhere (also on the driven row) and a perturbed
-    lattice; 128-wide and 256-wide units, partial last row-tiles."""
+    """float4 path (nx % 128 == 0) with random solids everywhere (also on the driven row) and a perturbed
+    lattice; one and several tile columns, partial last tile rows, ghost row alone in the last tile row."""
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 30, seed=nx + ny, solid_frac=0.1)
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30)
 
 
 @pytest.mark.parametrize("nx,ny", [(128, 3), (256, 64), (1024, 9), (384, 20)])
-def test_ldg_float4_kernel_random(oracle, lbm, nx, ny, monkeypatch):
-    """The register-path float4 kernel (kept beside the TMA kernel as the measured alternative)."""
-    monkeypatch.setenv("LBM_B200_KERNEL", "ldg")
+def test_scalar_kernel_on_vectorisable_sizes(oracle, lbm, nx, ny, monkeypatch):
+    """The any-width kernel forced onto sizes the float4 kernel normally takes: both must give the same bits."""
+    monkeypatch.setenv("LBM_B200_KERNEL", "scalar")
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 30, seed=nx * 7 + ny, solid_frac=0.1)
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == "vec4"
+        assert s.kernel_variant == "scalar"
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30)
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30, devices=[0, 0])
-
-
-@pytest.mark.parametrize("stages", [2, 4, 6])
-def test_tma_pipeline_depths(oracle, lbm, stages, monkeypatch):
-    """Every supported TMA pipeline depth gives the same lattice (more units than stages per CTA)."""
-    monkeypatch.setenv("LBM_B200_STAGES", str(stages))
-    monkeypatch.setenv("LBM_B200_BLOCKS_PER_SM", "1")
-    p, op, cells, obst = _random_problem(oracle, lbm, 512, 2500, 6, seed=stages, solid_frac=0.02)
-    with lbm.Solver(p) as s:
-        assert s.kernel_variant == "tma"
-    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 6)
 
 
 def test_run_in_pieces_equals_one_run(oracle, lbm):
@@ -109,7 +101,7 @@ def test_run_in_pieces_equals_one_run(oracle, lbm):
 
 
 @pytest.mark.parametrize("slabs", [2, 3, 4])
-@pytest.mark.parametrize("nx,ny", [(256, 64), (100, 19)])
+@pytest.mark.parametrize("nx,ny", [(256, 64), (100, 19), (128, 13), (384, 31)])
 def test_multi_slab_on_one_gpu_bit_exact(oracle, lbm, slabs, nx, ny):
     """Row-slab decomposition with writer-filled ghost rows and epoch flags, all slabs on GPU 0 (kernels
     run back to back on one stream).  The lattice must not depend on the decomposition."""
