@@ -21,6 +21,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "launch list rc=$?"
 echo "== ncu full (sweep kernel)"
 timeout 600 $CMD > $OUT/plain2.log 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 2 -f -o $OUT/sweep $CMD > $OUT/ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -f -o $OUT/sweep $CMD > $OUT/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT
