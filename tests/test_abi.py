@@ -1,0 +1,93 @@
+"""The drop-in boundary on a machine WITHOUT a GPU: liblbm_b200.so loads, exports every symbol that
+include/lbm_b200.h declares (and nothing undeclared with the lbm_ prefix), reports errors through codes
+instead of exceptions, and refuses to compute -- there is no CPU path to fall back to."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "lbm_b200.h")
+HOST_HEADER = os.path.join(ROOT, "include", "lbm_host.h")
+
+
+def declared_functions(path):
+    text = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(lbm_[a-z0-9_]+)\s*\(", text)))
+
+
+def exported_functions(lib_path, prefix):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    return sorted(line.split()[-1] for line in out.splitlines() if " T " in line and line.split()[-1].startswith(prefix))
+
+
+def test_header_and_library_agree(lbm):
+    declared = declared_functions(HEADER)
+    assert len(declared) >= 20
+    assert declared == sorted(lbm.ABI_SYMBOLS), "lbm-graphcore_b200/__init__.py ABI_SYMBOLS is out of sync with the header"
+    assert exported_functions(lbm.LIB_PATH, "lbm_") == declared
+    for name in declared:
+        assert hasattr(lbm.lib, name)
+    assert lbm.lib.lbm_abi_version() == int(re.search(r"#define LBM_B200_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
+
+
+def test_host_library_exports_its_header(lbm):
+    declared = declared_functions(HOST_HEADER)
+    assert declared == exported_functions(lbm.HOST_LIB_PATH, "lbm_host_")
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary must be consumable from C (cgo / JNI / ctypes style bindings): compile it with gcc -std=c99."""
+    src = tmp_path / "use.c"
+    src.write_text('#include "lbm_b200.h"\n#include "lbm_host.h"\nint main(void) { lbm_handle *h = 0; (void)h; return LBM_OK; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
+                    str(tmp_path / "use.o")], check=True, capture_output=True)
+
+
+def test_no_gpu_means_loud_failure_not_a_cpu_fallback(lbm):
+    if lbm.device_count() > 0:
+        pytest.skip("a CUDA device is visible here")
+    p = lbm.Params(128, 128, 10, 10, 0.1, 0.005, 1.85)
+    with pytest.raises(lbm.LbmError) as e:
+        lbm.Solver(p)
+    assert e.value.code == -2 and "CUDA" in str(e.value)
+    n = ctypes.c_int(7)
+    assert lbm.lib.lbm_device_count(ctypes.byref(n)) == -2 and n.value == 0
+    c = (ctypes.c_ulonglong * 7)()
+    assert lbm.lib.lbm_selftest_math(0, 16, c) == -2
+    # the driver binary fails the same way
+    gold = os.path.join(ROOT, "tests", "golden", "params")
+    r = subprocess.run([lbm.RUNNER_PATH, "--params", os.path.join(gold, "input_128x128.params"), "--obstacles",
+                        os.path.join(gold, "obstacles_128x128.dat")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU path" in r.stderr
+
+
+def test_argument_errors_do_not_need_a_gpu(lbm):
+    h = ctypes.c_void_p()
+    assert lbm.lib.lbm_create(ctypes.byref(h), 0, 5, 1, 0.1, 0.005, 1.85, 1) != 0 and not h.value
+    assert lbm.lib.lbm_create(ctypes.byref(h), 128, 128, 1, 0.1, 0.005, 1.85, 0) == -1
+    assert b"num_gpus" in lbm.lib.lbm_last_error()
+    assert lbm.lib.lbm_run(None, 1) == -1 and lbm.lib.lbm_upload(None, None, None) == -1
+    assert lbm.lib.lbm_download(None, None, None) == -1
+    lbm.lib.lbm_destroy(None)  # harmless
+    assert lbm.lib.lbm_ipc_blob_bytes() >= 64
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing in the product package or the C ABI sources may reference it."""
+    pkg = os.path.join(ROOT, "lbm-graphcore_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(base, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle|#\s*include\s*[<\"][^>\"]*oracle|(CDLL|dlopen)\([^)]*oracle|-llbm_oracle",
+                             text, flags=re.M):
+                    offenders.append(os.path.join(base, f))
+    assert not offenders, offenders
+    ldd = subprocess.run(["ldd", os.path.join(pkg, "liblbm_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "torch" not in ldd
