@@ -121,6 +121,12 @@ int lbm_rows(lbm_handle *h, int *row_begin, int *row_count);
  * step done).  av_vels[t] = (float)(sum over ranks, in rank order) / (float)(total free cells). */
 int lbm_download_tot_u(lbm_handle *h, double *tot_u);
 
+/* The four computed columns of final_state.dat -- u_x, u_y, u, pressure per cell, float[rows][nx][4] -- evaluated
+ * on the device from the current state with the arithmetic of lbm::writeResults
+ * (main/include/LatticeBoltzmannUtils.hpp:240-267): 16 bytes per cell cross PCIe instead of the 36-byte cell, and
+ * the host only has to format text.  Rows as for lbm_download. */
+int lbm_download_fields(lbm_handle *h, float *fields);
+
 /* Self-test of the kernels' IEEE division / square-root helpers against CUDA's __fdiv_rn / __fsqrt_rn on
  * GPU `device`: exhaustive for x/9, x/36 and sqrt(x), `pairs` random operand pairs for a/b.
  * counts[7] = {x/9 mismatches, sqrt mismatches, a/b mismatches, x/36 mismatches, #x/9, #sqrt, #a/b}. */

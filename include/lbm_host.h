@@ -39,6 +39,11 @@ int lbm_host_write_av_vels(const char *path, const float *av_vels, long long n);
 int lbm_host_write_final_state(const char *path, long long nx, long long ny, float density, const float *cells,
                                const uint8_t *obstacles);
 
+/* The same file from fields the device already evaluated (lbm_download_fields of lbm_b200.h): fields is
+ * float[ny][nx][4] = u_x, u_y, u, pressure.  Lines are formatted on `threads` host threads (0 = all cores). */
+int lbm_host_write_final_state_fields(const char *path, long long nx, long long ny, const float *fields,
+                                      const uint8_t *obstacles, int threads);
+
 /* the synthetic channel of SURVEY.md 8(d): rows [row_begin, row_begin+row_count) of an nx*ny grid */
 int lbm_host_synthetic_obstacles(long long nx, long long ny, uint64_t seed, float solid_prob, long long row_begin,
                                  long long row_count, uint8_t *obstacles);

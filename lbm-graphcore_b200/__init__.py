@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_create_rank", "lbm_ipc_blob_bytes",
-    "lbm_ipc_export", "lbm_ipc_connect", "lbm_selftest_math",
+    "lbm_ipc_export", "lbm_ipc_connect", "lbm_selftest_math", "lbm_download_fields",
 )
 
 
@@ -66,6 +66,7 @@ def _load() -> ctypes.CDLL:
     lib.lbm_run.argtypes = [c_void_p, c_int]
     lib.lbm_download.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.lbm_download_tot_u.argtypes = [c_void_p, c_void_p]
+    lib.lbm_download_fields.argtypes = [c_void_p, c_void_p]
     lib.lbm_elapsed_ms.argtypes = [c_void_p, P(ctypes.c_double)]
     lib.lbm_destroy.argtypes = [c_void_p]
     lib.lbm_destroy.restype = None
@@ -187,6 +188,12 @@ class Solver:
 
     def download_raw(self, cells_ptr: int, av_vels_ptr: int) -> None:
         _check(lib.lbm_download(self._h, cells_ptr, av_vels_ptr))
+
+    def download_fields(self) -> np.ndarray:
+        """u_x, u_y, u, pressure per cell, computed on the device: float32[rows, nx, 4]."""
+        f = np.empty((self.row_count, self.params.nx, 4), dtype=np.float32)
+        _check(lib.lbm_download_fields(self._h, f.ctypes.data))
+        return f
 
     def download_tot_u(self) -> np.ndarray:
         t = np.zeros(max(self.steps_done, 1), dtype=np.float64)

@@ -681,6 +681,30 @@ int lbm_download(lbm_handle *h, float *cells_aos, float *av_vels) {
   return LBM_OK;
 }
 
+int lbm_download_fields(lbm_handle *h, float *fields) {
+  if (!h || !fields) return fail(LBM_E_ARG, "null argument");
+  if (!h->uploaded) return fail(LBM_E_STATE, "lbm_download_fields before lbm_upload");
+  const int nx = h->nx;
+  if ((size_t)nx * 4 * sizeof(float) > kStageBytes)
+    return fail(LBM_E_ARG, "a single row of %d cells does not fit the staging buffer", nx);
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
+    float *out = fields + first * nx * 4;
+    const int rows_per_chunk = (int)std::max<size_t>(1, kStageBytes / ((size_t)nx * 4 * sizeof(float)));
+    for (int r = 0; r < s.nyl; r += rows_per_chunk) {
+      const int rows = std::min(rows_per_chunk, s.nyl - r);
+      lbm::final_state_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(s.buf[h->cur], s.mask, reinterpret_cast<float4 *>(s.stage),
+                                                                          h->ntx, nx, rows, 1 + r, h->density);
+      ++h->launches;
+      KERNEL_CHECK(s.stream, "final_state");
+      CUDA_TRY(cudaMemcpyAsync(out + (size_t)r * nx * 4, s.stage, (size_t)rows * nx * 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+      CUDA_TRY(cudaStreamSynchronize(s.stream));
+    }
+  }
+  return LBM_OK;
+}
+
 // ---- introspection -------------------------------------------------------------------------------
 int lbm_steps_done(lbm_handle *h, int *steps) {
   if (!h || !steps) return fail(LBM_E_ARG, "null argument");

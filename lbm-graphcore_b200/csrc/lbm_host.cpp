@@ -84,6 +84,14 @@ int lbm_host_write_final_state(const char *path, long long nx, long long ny, flo
   return lbm::writeResults(path, make_params(nx, ny, density), o, c) ? 0 : -2;
 }
 
+int lbm_host_write_final_state_fields(const char *path, long long nx, long long ny, const float *fields,
+                                      const uint8_t *obstacles, int threads) {
+  if (!path || !fields || !obstacles || nx < 1 || ny < 1 || threads < 0) return -1;
+  lbm::Obstacles o(static_cast<size_t>(nx), static_cast<size_t>(ny));
+  std::memcpy(o.getData(), obstacles, static_cast<size_t>(nx) * static_cast<size_t>(ny));
+  return lbm::writeResultsFromFields(path, make_params(nx, ny, 0.f), o, fields, static_cast<unsigned>(threads)) ? 0 : -2;
+}
+
 int lbm_host_synthetic_obstacles(long long nx, long long ny, uint64_t seed, float solid_prob, long long row_begin,
                                  long long row_count, uint8_t *obstacles) {
   if (!obstacles || nx < 1 || ny < 1 || row_begin < 0 || row_count < 0 || row_begin + row_count > ny) return -1;

@@ -18,7 +18,10 @@
 #include <iostream>
 #include <memory>
 #include <optional>
+#include <algorithm>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace lbm {
@@ -249,23 +252,69 @@ inline CellFields cellFields(const float *s, bool solid, float density) {
   return {u_x, u_y, sqrtf((u_x * u_x) + (u_y * u_y)), local_density * c_sq};
 }
 
-// "<ii> <jj> <u_x> <u_y> <u> <pressure> <obstacle>\n", jj outer, ii inner (LatticeBoltzmannUtils.hpp:221-281)
-inline bool writeResults(const std::string &filename, const Params &params, const Obstacles &obstacles,
-                         const Cells &cells) {
-  detail::TextSink out(filename);
-  if (!out.ok()) return false;
-  for (size_t jj = 0; jj < params.ny; ++jj) {
-    for (size_t ii = 0; ii < params.nx; ++ii) {
-      const bool solid = obstacles.at(ii, jj);
-      const CellFields f = cellFields(&cells.data[(ii + jj * params.nx) * NumSpeeds], solid, params.density);
-      char *p = out.reserve(160);
-      const int n = std::snprintf(p, 160, "%zu %zu %.12e %.12e %.12e %.12e %d\n", ii, jj, static_cast<double>(f.u_x),
-                                  static_cast<double>(f.u_y), static_cast<double>(f.u),
-                                  static_cast<double>(f.pressure), solid ? 1 : 0);
-      out.commit(160, static_cast<size_t>(n));
+namespace detail {
+// Formats rows [0, ny) of final_state.dat with `line(ii, jj)` -> CellFields on all host cores: the rows are cut into
+// chunks, each wave of chunks is formatted in parallel into per-thread buffers and written in row order.  The
+// reference streams one line at a time through an ofstream with std::endl (a flush per line,
+// LatticeBoltzmannUtils.hpp:274); at 1024x1024 that costs more than the whole GPU solve.
+template <typename FieldsAt>
+bool writeFinalStateRows(const std::string &filename, const Params &params, const Obstacles &obstacles, FieldsAt fields_at,
+                         unsigned threads = 0) {
+  std::FILE *fp = std::fopen(filename.c_str(), "w");
+  if (!fp) return false;
+  if (threads == 0) threads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  const size_t rows_per_chunk = std::max<size_t>(1, (size_t(1) << 16) / std::max<size_t>(params.nx, 1));
+  const size_t chunks = (params.ny + rows_per_chunk - 1) / rows_per_chunk;
+  std::vector<std::string> bufs(std::min<size_t>(threads, std::max<size_t>(chunks, 1)));
+  bool ok = true;
+  auto format_chunk = [&](size_t chunk, std::string &out) {
+    out.clear();
+    const size_t j0 = chunk * rows_per_chunk, j1 = std::min(params.ny, j0 + rows_per_chunk);
+    out.reserve((j1 - j0) * params.nx * 96);
+    char line[192];
+    for (size_t jj = j0; jj < j1; ++jj) {
+      for (size_t ii = 0; ii < params.nx; ++ii) {
+        const bool solid = obstacles.at(ii, jj);
+        const CellFields f = fields_at(ii, jj, solid);
+        const int n = std::snprintf(line, sizeof line, "%zu %zu %.12e %.12e %.12e %.12e %d\n", ii, jj, static_cast<double>(f.u_x),
+                                    static_cast<double>(f.u_y), static_cast<double>(f.u), static_cast<double>(f.pressure),
+                                    solid ? 1 : 0);
+        out.append(line, static_cast<size_t>(n));
+      }
     }
+  };
+  for (size_t base = 0; base < chunks && ok; base += bufs.size()) {
+    const size_t n = std::min(bufs.size(), chunks - base);
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < n; ++t) pool.emplace_back(format_chunk, base + t, std::ref(bufs[t]));
+    format_chunk(base, bufs[0]);
+    for (auto &th : pool) th.join();
+    for (size_t t = 0; t < n && ok; ++t) ok = std::fwrite(bufs[t].data(), 1, bufs[t].size(), fp) == bufs[t].size();
   }
-  return out.close();
+  if (std::fclose(fp) != 0) ok = false;
+  return ok;
+}
+}  // namespace detail
+
+// "<ii> <jj> <u_x> <u_y> <u> <pressure> <obstacle>\n", jj outer, ii inner (LatticeBoltzmannUtils.hpp:221-281)
+inline bool writeResults(const std::string &filename, const Params &params, const Obstacles &obstacles, const Cells &cells,
+                         unsigned threads = 0) {
+  return detail::writeFinalStateRows(
+      filename, params, obstacles,
+      [&](size_t ii, size_t jj, bool solid) { return cellFields(&cells.data[(ii + jj * params.nx) * NumSpeeds], solid, params.density); },
+      threads);
+}
+
+// Same file from fields already evaluated on the device (lbm_download_fields): float[ny][nx][4] = u_x, u_y, u, pressure
+inline bool writeResultsFromFields(const std::string &filename, const Params &params, const Obstacles &obstacles,
+                                   const float *fields, unsigned threads = 0) {
+  return detail::writeFinalStateRows(
+      filename, params, obstacles,
+      [&](size_t ii, size_t jj, bool) {
+        const float *f = fields + (ii + jj * params.nx) * 4;
+        return CellFields{f[0], f[1], f[2], f[3]};
+      },
+      threads);
 }
 
 }  // namespace lbm

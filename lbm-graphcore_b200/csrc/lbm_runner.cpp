@@ -9,7 +9,7 @@
 //   device-side timer (:133-144).
 //
 //   lbm_runner --params FILE --obstacles FILE [-n|--num-gpus N] [-d|--debug]
-//              [--iters N] [--outdir DIR] [--no-output] [--reruns N]
+//              [--iters N] [--outdir DIR] [--no-output] [--download-cells] [--reruns N]
 //              [--synthetic NXxNY --solid-prob P --seed S --iters N]
 //   (--num-ipus, --device and --exe of the reference are accepted; the latter two are ignored: there
 //   is no separately compiled graph to deserialise.)
@@ -40,7 +40,7 @@ double timedStep(const std::string &description, F f) {
 struct Options {
   std::string params, obstacles, outdir = ".";
   int num_gpus = 1;
-  bool debug = false, no_output = false;
+  bool debug = false, no_output = false, download_cells = false;
   long iters = -1;
   int reruns = 5;
   bool synthetic = false;
@@ -60,6 +60,7 @@ void usage(const char *exe) {
             << "      --iters arg        run this many timesteps instead of maxIters\n"
             << "      --outdir arg       where av_vels.dat and final_state.dat go (default: .)\n"
             << "      --no-output        skip final_state.dat (av_vels.dat is still written)\n"
+            << "      --download-cells   copy the whole lattice back and derive final_state.dat on the host (reference way)\n"
             << "      --reruns arg       timed re-runs after the main run (default: 5)\n"
             << "      --synthetic NXxNY  generate the synthetic channel instead of reading files\n"
             << "      --solid-prob arg   random solid fraction of the synthetic channel (default: 0.01)\n"
@@ -84,6 +85,7 @@ bool parse(int argc, char **argv, Options &o) {
     const char *s = nullptr;
     if (a == "-d" || a == "--debug") o.debug = true;
     else if (a == "--no-output") o.no_output = true;
+    else if (a == "--download-cells") o.download_cells = true;
     else if (a == "--params") { if (!(s = value())) return false; o.params = s; }
     else if (a == "--obstacles") { if (!(s = value())) return false; o.obstacles = s; }
     else if (a == "-n" || a == "--num-gpus" || a == "--num-ipus") { if (!(s = value())) return false; o.num_gpus = std::atoi(s); }
@@ -161,6 +163,7 @@ int main(int argc, char *argv[]) {
 
   double total_compute_time = 0.0;
   const bool keep_cells = !opt.synthetic;  // the synthetic channel lives on the device only
+  const bool want_final_state = keep_cells && !opt.no_output;
   auto cells = lbm::Cells(keep_cells ? params->nx : 0, keep_cells ? params->ny : 0);
   if (keep_cells) cells.initialise(*params);
   auto av_vels = std::vector<float>(params->maxIters, 0.0f);
@@ -184,15 +187,22 @@ int main(int argc, char *argv[]) {
   double device_ms = 0.0;
   lbm_elapsed_ms(engine, &device_ms);
 
+  // run(2).  The reference streams the whole AoS lattice back and derives u_x, u_y, u and pressure on the host
+  // (main/LbmRunner.cpp:106-112); here the device evaluates those four columns (16 instead of 36 bytes per cell
+  // cross PCIe) unless --download-cells asks for the reference's behaviour.
+  std::vector<float> fields;
+  if (want_final_state && !opt.download_cells) fields.resize(params->nx * params->ny * 4);
   timedStep("Running copy to host step", [&]() {
-    rc = lbm_download(engine, keep_cells ? cells.data.data() : nullptr, av_vels.data());
+    rc = lbm_download(engine, (want_final_state && opt.download_cells) ? cells.data.data() : nullptr, av_vels.data());
+    if (rc == LBM_OK && !fields.empty()) rc = lbm_download_fields(engine, fields.data());
   });
   if (rc != LBM_OK) return die("copy to host");
   av_vels.resize(iters);
 
   timedStep("Writing output files ", [&]() {
     lbm::writeAverageVelocities(opt.outdir + "/av_vels.dat", av_vels);
-    if (keep_cells && !opt.no_output) lbm::writeResults(opt.outdir + "/final_state.dat", *params, *obstacles, cells);
+    if (!fields.empty()) lbm::writeResultsFromFields(opt.outdir + "/final_state.dat", *params, *obstacles, fields.data());
+    else if (want_final_state) lbm::writeResults(opt.outdir + "/final_state.dat", *params, *obstacles, cells);
   });
 
   const double cell_updates = static_cast<double>(params->nx) * static_cast<double>(params->ny) * static_cast<double>(iters);

@@ -43,6 +43,15 @@ def test_lbm_runner_full_run_passes_check(lbm, case, tmp_path):
     s = int(fx["stride"])
     pressure = fs[:, 2].astype(np.float32).reshape(p.ny, p.nx)[::s, ::s]
     assert np.array_equal(pressure, fx["pressure"])
+    if case == "128x128":
+        # the reference's way (whole lattice back, fields on the host) writes the same bytes
+        other = tmp_path / "cells_way"
+        other.mkdir()
+        r2 = subprocess.run([lbm.RUNNER_PATH, "--params", params_path(case), "--obstacles", obstacles_path(case), "--outdir",
+                             str(other), "--reruns", "0", "--download-cells"], capture_output=True, text=True, timeout=900)
+        assert r2.returncode == 0
+        assert (other / "final_state.dat").read_bytes() == (tmp_path / "final_state.dat").read_bytes()
+        assert (other / "av_vels.dat").read_bytes() == (tmp_path / "av_vels.dat").read_bytes()
 
 
 @pytest.mark.parametrize("case", CASES)

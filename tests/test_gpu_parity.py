@@ -127,6 +127,23 @@ def test_synthetic_channel_matches_host_twin(oracle, lbm):
     assert ulp_distance(got_av, want_av).max() <= 1
 
 
+@pytest.mark.parametrize("nx,ny,devices", [(256, 40, None), (100, 19, None), (384, 31, [0, 0, 0])])
+def test_device_final_state_fields_equal_host_fields(oracle, lbm, nx, ny, devices):
+    """lbm_download_fields (u_x, u_y, u, pressure evaluated on the GPU) == the oracle's / host writer's fields, bit
+    for bit, obstacle cells included (u = 0, pressure = density/3)."""
+    p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 20, seed=nx + 3 * ny, solid_frac=0.1)
+    kw = {"devices": devices} if devices else {}
+    with lbm.Solver(p, **kw) as s:
+        s.upload(cells, obst)
+        s.run(20)
+        got_cells, _ = s.download(av_vels=False)
+        fields = s.download_fields()
+    ux, uy, u, pr = oracle.final_state_fields(op, got_cells, obst)
+    want = np.stack([ux, uy, u, pr], axis=-1).astype(np.float32)
+    assert fields.shape == want.shape
+    assert np.array_equal(fields.view(np.uint32), want.view(np.uint32))
+
+
 def test_division_and_sqrt_helpers_match_ieee_library(lbm):
     """The kernels replace __fdiv_rn/__fsqrt_rn by the library's own fast-path sequence under a wider
     guard (zero numerators, sqrt(0)).  Exhaustive for rho/9, rho/36 and sqrt; 2^30 random pairs for a/b."""

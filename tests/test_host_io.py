@@ -27,6 +27,7 @@ def host(lbm):
     L.lbm_host_reynolds_number.restype = f
     L.lbm_host_write_av_vels.argtypes = [ctypes.c_char_p, vp, ll]
     L.lbm_host_write_final_state.argtypes = [ctypes.c_char_p, ll, ll, f, vp, vp]
+    L.lbm_host_write_final_state_fields.argtypes = [ctypes.c_char_p, ll, ll, vp, vp, ctypes.c_int]
     L.lbm_host_synthetic_obstacles.argtypes = [ll, ll, ctypes.c_uint64, f, ll, ll, vp]
     return L
 
@@ -127,3 +128,22 @@ def test_synthetic_channel_host_and_numpy_twins_agree(host, lbm):
     assert np.array_equal(got, full[50:70])
     assert np.array_equal(lbm.synthetic_obstacles(nx, ny, 1234, 0.01, 50, 20), full[50:70])
     assert full[0].all() and full[-1].all() and not full[ny - 2].any()
+
+
+def test_fields_writer_and_threaded_formatting_give_the_same_bytes(host, oracle, tmp_path):
+    """final_state.dat from device-style fields (u_x, u_y, u, pressure per cell) on 1, 3 and all threads must be
+    byte-identical to the cells-based writer (the writer, not the solve, dominates 1024^2)."""
+    p = oracle.make_params(300, 70, 1, 10, 0.1, 0.005, 1.85)
+    rng = np.random.default_rng(5)
+    cells = (oracle.init_cells(p) * (1 + 0.3 * rng.random((70, 300, 9)))).astype(np.float32)
+    obst = (rng.random((70, 300)) < 0.1).astype(np.uint8)
+    ref = str(tmp_path / "cells.dat")
+    assert host.lbm_host_write_final_state(ref.encode(), 300, 70, 0.1, cells.ctypes.data, obst.ctypes.data) == 0
+    ux, uy, u, pr = oracle.final_state_fields(p, cells, obst)
+    fields = np.ascontiguousarray(np.stack([ux, uy, u, pr], axis=-1), dtype=np.float32)
+    want = open(ref, "rb").read()
+    assert want.count(b"\n") == 300 * 70
+    for threads in (1, 3, 0):
+        out = str(tmp_path / f"fields{threads}.dat")
+        assert host.lbm_host_write_final_state_fields(out.encode(), 300, 70, fields.ctypes.data, obst.ctypes.data, threads) == 0
+        assert open(out, "rb").read() == want
