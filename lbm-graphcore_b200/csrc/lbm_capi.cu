@@ -221,16 +221,35 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   return a;
 }
 
-int launch_sweep(lbm_handle *h, Slab &s) {
+template <typename K>
+cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, bool pdl, const lbm::SweepArgs &a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(32, lbm::kTileH, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+// One timestep of one slab.  `overlap` = this launch directly follows another sweep of the same slab in the
+// stream, so it may be scheduled while that one drains (programmatic dependent launch; LBM_B200_PDL=0 disables).
+int launch_sweep(lbm_handle *h, Slab &s, bool overlap) {
+  static const bool pdl_enabled = !(getenv("LBM_B200_PDL") && atoi(getenv("LBM_B200_PDL")) == 0);
   const lbm::SweepArgs a = sweep_args(h, s);
-  const dim3 block(32, lbm::kTileH, 1);
-  if (s.kernel == KERNEL_VEC4) {
-    if (h->multi) lbm::sweep_kernel<true, true><<<s.grid, block, 0, s.stream>>>(a);
-    else lbm::sweep_kernel<true, false><<<s.grid, block, 0, s.stream>>>(a);
-  } else {
-    if (h->multi) lbm::sweep_kernel<false, true><<<s.grid, block, 0, s.stream>>>(a);
-    else lbm::sweep_kernel<false, false><<<s.grid, block, 0, s.stream>>>(a);
-  }
+  const bool pdl = overlap && pdl_enabled;
+  cudaError_t e;
+  if (s.kernel == KERNEL_VEC4)
+    e = h->multi ? launch_pdl(lbm::sweep_kernel<true, true>, s.grid, s.stream, pdl, a)
+                 : launch_pdl(lbm::sweep_kernel<true, false>, s.grid, s.stream, pdl, a);
+  else
+    e = h->multi ? launch_pdl(lbm::sweep_kernel<false, true>, s.grid, s.stream, pdl, a)
+                 : launch_pdl(lbm::sweep_kernel<false, false>, s.grid, s.stream, pdl, a);
+  if (e != cudaSuccess) return fail(LBM_E_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
   ++h->launches;
   KERNEL_CHECK(s.stream, "sweep");
   return LBM_OK;
@@ -591,10 +610,15 @@ int lbm_run(lbm_handle *h, int iters) {
     h->first_run_pending = false;
   }
   // one launch per slab per timestep, slabs interleaved so no GPU's queue runs ahead of its neighbours
+  // slabs that share a stream (several slabs on one device) alternate in it, so a sweep is not preceded by a
+  // sweep of the same slab: no dependent-launch overlap there (the flag waits need the other slab to finish)
+  bool shared_stream = false;
+  for (size_t i = 0; i < h->slabs.size(); ++i)
+    for (size_t j = 0; j < i; ++j) shared_stream |= (h->slabs[i].stream == h->slabs[j].stream);
   for (int t = 0; t < iters; ++t) {
     for (Slab &s : h->slabs) {
       if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
-      int rc = launch_sweep(h, s);
+      int rc = launch_sweep(h, s, t > 0 && !shared_stream);
       if (rc) return rc;
     }
     h->cur ^= 1;

@@ -5,6 +5,6 @@ G=tests/golden/params
 for mode in "" "--download-cells"; do
   for c in 256x256 1024x1024; do
     echo "== $c $mode" | tee -a $OUT/runner_times.txt
-    ( /usr/bin/time -f "wall %e s" lbm-graphcore_b200/bin/lbm_runner --params $G/input_$c.params --obstacles $G/obstacles_$c.dat --outdir /tmp --reruns 1 -d $mode ) 2>&1 | grep -v "^$" | tee -a $OUT/runner_times.txt
+    ( TIMEFORMAT="wall %R s"; time lbm-graphcore_b200/bin/lbm_runner --params $G/input_$c.params --obstacles $G/obstacles_$c.dat --outdir /tmp --reruns 1 -d $mode ) 2>&1 | grep -v "^$" | tee -a $OUT/runner_times.txt
   done
 done
