@@ -195,6 +195,7 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   a.north_dst = s.north_buf[c ^ 1];
   a.south_dst = s.south_buf[c ^ 1];
   a.mask = s.mask;
+  a.lattice_floats = h->lattice_floats;
   a.ntx = h->ntx;
   a.tiles_y = s.tiles_y;
   a.nx = h->nx;
