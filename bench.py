@@ -163,6 +163,26 @@ def cpu_baseline(nx, ny, budget_s, lbm_mod):
                       f"-ffp-contract=off, OpenMP over rows, fp64 tot_u), {dt:.1f} s"}
 
 
+def reference_program_baseline():
+    """The UNMODIFIED reference program (oracle/_ref/compareLbm_fma = main/LastChance.cpp built with the reference's
+    own flags, -O3 and FMA contraction allowed) on the reference's own CPU-runnable case, BASELINE.json configs[0]:
+    input_128x128, 40 000 timesteps, single-threaded as shipped.  None when oracle/_ref was never built."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "compareLbm_fma")
+    gold = os.path.join(ROOT, "tests", "golden", "params")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, os.path.join(gold, "input_128x128.params"), os.path.join(gold, "obstacles_128x128.dat")],
+                           cwd=tmp, capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0 or not os.path.exists(os.path.join(tmp, "av_vels.dat")):
+            return None
+    return {"value": round(128 * 128 * 40000 / dt / 1e6, 2), "unit": "MLUPS", "cores": 1, "kind": "reference",
+            "sample": f"unmodified main/LastChance.cpp (g++ -O3 -march=x86-64-v3), params/input_128x128.params, 40000 timesteps "
+                      f"incl. its file output, {dt:.1f} s wall"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The unmodified
     program (oracle/_ref/compareLbm_*) always writes final_state.dat (25 GB of text at 16384^2) and is
@@ -358,6 +378,9 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(nx, ny, args.cpu_seconds, lbm)
+        ref = reference_program_baseline()
+        if ref is not None:
+            line["cpu_baseline"]["reference_program"] = ref
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

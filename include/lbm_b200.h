@@ -114,6 +114,11 @@ int lbm_create_on_devices(lbm_handle **out, int nx, int ny, int max_iters, float
  * (main/include/LatticeBoltzmannUtils.hpp:137-157).  Equivalent to lbm_upload of those arrays. */
 int lbm_init_synthetic(lbm_handle *h, uint64_t seed, float solid_prob);
 
+/* Partition diagnostics (what main/TileMappingStats.cpp reports for IPU tiles, here per row slab): how many slabs
+ * this handle drives, and for each its GPU, its global rows and its non-obstacle cells (-1 before an upload). */
+int lbm_slab_count(lbm_handle *h, int *count);
+int lbm_slab_info(lbm_handle *h, int slab, int *device, int *row_begin, int *row_count, long long *free_cells);
+
 /* the rows this handle owns: global rows [row_begin, row_begin + row_count) */
 int lbm_rows(lbm_handle *h, int *row_begin, int *row_count);
 

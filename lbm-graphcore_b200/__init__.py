@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_create_rank", "lbm_ipc_blob_bytes",
-    "lbm_ipc_export", "lbm_ipc_connect", "lbm_selftest_math", "lbm_download_fields",
+    "lbm_ipc_export", "lbm_ipc_connect", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
 )
 
 
@@ -67,6 +67,8 @@ def _load() -> ctypes.CDLL:
     lib.lbm_download.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.lbm_download_tot_u.argtypes = [c_void_p, c_void_p]
     lib.lbm_download_fields.argtypes = [c_void_p, c_void_p]
+    lib.lbm_slab_count.argtypes = [c_void_p, P(c_int)]
+    lib.lbm_slab_info.argtypes = [c_void_p, c_int, P(c_int), P(c_int), P(c_int), P(ctypes.c_longlong)]
     lib.lbm_elapsed_ms.argtypes = [c_void_p, P(ctypes.c_double)]
     lib.lbm_destroy.argtypes = [c_void_p]
     lib.lbm_destroy.restype = None
@@ -224,6 +226,18 @@ class Solver:
         n = ctypes.c_longlong()
         _check(lib.lbm_launch_count(self._h, ctypes.byref(n)))
         return n.value
+
+    @property
+    def slabs(self) -> list[dict]:
+        """Per row slab: GPU, global rows, non-obstacle cells (the partition diagnostics of lbm_slab_info)."""
+        n = ctypes.c_int()
+        _check(lib.lbm_slab_count(self._h, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            d, r0, rc, fc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
+            _check(lib.lbm_slab_info(self._h, i, ctypes.byref(d), ctypes.byref(r0), ctypes.byref(rc), ctypes.byref(fc)))
+            out.append({"device": d.value, "row_begin": r0.value, "row_count": rc.value, "free_cells": fc.value})
+        return out
 
     @property
     def kernel_variant(self) -> str:

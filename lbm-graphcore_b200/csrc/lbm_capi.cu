@@ -54,6 +54,10 @@ struct Slab {
   int nyl = 0;   // owned rows
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
+  // upload/download pipeline: the staging buffer is used as two halves; PCIe copies run on copy_stream while the
+  // transposition kernel of the other half runs on `stream`
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t filled[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
   // one exported allocation: [lattice 0][lattice 1][flags]
   char *base = nullptr;
   float *buf[2] = {nullptr, nullptr};
@@ -146,6 +150,11 @@ int alloc_slab(lbm_handle *h, Slab &s) {
   CUDA_TRY(cudaMalloc((void **)&s.stage, kStageBytes));
   CUDA_TRY(cudaEventCreate(&s.ev0));
   CUDA_TRY(cudaEventCreate(&s.ev1));
+  CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CUDA_TRY(cudaEventCreateWithFlags(&s.filled[b], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.drained[b], cudaEventDisableTiming));
+  }
   return LBM_OK;
 }
 
@@ -153,6 +162,11 @@ void free_slab(Slab &s) {
   cudaSetDevice(s.device);
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
+  for (int b = 0; b < 2; ++b) {
+    if (s.filled[b]) cudaEventDestroy(s.filled[b]);
+    if (s.drained[b]) cudaEventDestroy(s.drained[b]);
+  }
+  if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
   cudaFree(s.stage);
   cudaFree(s.free_dev);
   cudaFree(s.step);
@@ -253,6 +267,53 @@ int launch_sweep(lbm_handle *h, Slab &s, bool overlap) {
   if (e != cudaSuccess) return fail(LBM_E_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
   ++h->launches;
   KERNEL_CHECK(s.stream, "sweep");
+  return LBM_OK;
+}
+
+// ---- staged host <-> device pipelines -------------------------------------------------------------
+// Rows travel in chunks through the two halves of the slab's staging buffer.  `chunk` counts chunks since the last
+// drain so that consecutive pipelines (cells, then obstacles) keep alternating halves correctly.
+constexpr size_t kHalfStage = kStageBytes / 2;
+
+// host -> staging half (copy_stream) -> `consume(stage_half, first_row, rows)` launches a kernel on s.stream
+template <typename Consume>
+int stage_in(Slab &s, const char *host, size_t row_bytes, int total_rows, int &chunk, Consume consume) {
+  if (row_bytes > kHalfStage) return fail(LBM_E_ARG, "a single row of %zu bytes does not fit the staging buffer", row_bytes);
+  const int rows_per_chunk = (int)std::max<size_t>(1, kHalfStage / row_bytes);
+  for (int r = 0; r < total_rows; r += rows_per_chunk, ++chunk) {
+    const int rows = std::min(rows_per_chunk, total_rows - r), b = chunk & 1;
+    char *half = reinterpret_cast<char *>(s.stage) + (size_t)b * kHalfStage;
+    if (chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.drained[b], 0));  // its previous user has read it
+    CUDA_TRY(cudaMemcpyAsync(half, host + (size_t)r * row_bytes, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, s.copy_stream));
+    CUDA_TRY(cudaEventRecord(s.filled[b], s.copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(s.stream, s.filled[b], 0));
+    int rc = consume(half, r, rows);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s.drained[b], s.stream));
+  }
+  return LBM_OK;
+}
+// `produce(stage_half, first_row, rows)` launches a kernel on s.stream -> staging half -> host (copy_stream)
+template <typename Produce>
+int stage_out(Slab &s, char *host, size_t row_bytes, int total_rows, int &chunk, Produce produce) {
+  if (row_bytes > kHalfStage) return fail(LBM_E_ARG, "a single row of %zu bytes does not fit the staging buffer", row_bytes);
+  const int rows_per_chunk = (int)std::max<size_t>(1, kHalfStage / row_bytes);
+  for (int r = 0; r < total_rows; r += rows_per_chunk, ++chunk) {
+    const int rows = std::min(rows_per_chunk, total_rows - r), b = chunk & 1;
+    char *half = reinterpret_cast<char *>(s.stage) + (size_t)b * kHalfStage;
+    if (chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(s.stream, s.drained[b], 0));  // its previous contents are on the host
+    int rc = produce(half, r, rows);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s.filled[b], s.stream));
+    CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.filled[b], 0));
+    CUDA_TRY(cudaMemcpyAsync(host + (size_t)r * row_bytes, half, (size_t)rows * row_bytes, cudaMemcpyDeviceToHost, s.copy_stream));
+    CUDA_TRY(cudaEventRecord(s.drained[b], s.copy_stream));
+  }
+  return LBM_OK;
+}
+int drain_stages(Slab &s) {
+  CUDA_TRY(cudaStreamSynchronize(s.copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
   return LBM_OK;
 }
 
@@ -518,35 +579,34 @@ int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles) 
     const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
     const float *cells = cells_aos + first * nx * lbm::kSpeeds;
     const uint8_t *obst = obstacles + first * nx;
-    // cells: AoS chunks of whole rows through the staging buffer
-    const int rows_per_chunk = (int)std::max<size_t>(1, kStageBytes / ((size_t)nx * lbm::kSpeeds * sizeof(float)));
-    if ((size_t)nx * lbm::kSpeeds * sizeof(float) > kStageBytes)
-      return fail(LBM_E_ARG, "a single row of %d cells does not fit the staging buffer", nx);
-    for (int r = 0; r < s.nyl; r += rows_per_chunk) {
-      const int rows = std::min(rows_per_chunk, s.nyl - r);
-      const size_t bytes = (size_t)rows * nx * lbm::kSpeeds * sizeof(float);
-      CUDA_TRY(cudaMemcpyAsync(s.stage, cells + (size_t)r * nx * lbm::kSpeeds, bytes, cudaMemcpyHostToDevice, s.stream));
-      lbm::aos_to_tiles_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(s.stage, s.buf[0], h->ntx, nx, rows, 1 + r);
-      ++h->launches;
-      KERNEL_CHECK(s.stream, "aos_to_soa");
-      // the staging buffer is reused: wait for the transposition before the next copy lands (a pageable
-      // source makes the copy synchronous anyway)
-      CUDA_TRY(cudaStreamSynchronize(s.stream));
-    }
-    // obstacles: bytes -> bits
-    const int rows_per_mchunk = (int)std::max<size_t>(1, kStageBytes / (size_t)nx);
+    // cells: AoS rows -> tiles; obstacles: bytes -> bits.  Chunks of whole rows, PCIe copy of one half of the
+    // staging buffer overlapped with the transposition of the other
+    int chunk = 0;
+    rc = stage_in(s, reinterpret_cast<const char *>(cells), (size_t)nx * lbm::kSpeeds * sizeof(float), s.nyl, chunk,
+                  [&](char *stage, int r, int rows) {
+                    lbm::aos_to_tiles_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(reinterpret_cast<const float *>(stage), s.buf[0],
+                                                                                        h->ntx, nx, rows, 1 + r);
+                    ++h->launches;
+                    KERNEL_CHECK(s.stream, "aos_to_tiles");
+                    return (int)LBM_OK;
+                  });
+    if (rc) return rc;
     const int words = (nx + 31) / 32;
-    uint8_t *stage8 = reinterpret_cast<uint8_t *>(s.stage);
-    for (int r = 0; r < s.nyl; r += rows_per_mchunk) {
-      const int rows = std::min(rows_per_mchunk, s.nyl - r);
-      CUDA_TRY(cudaMemcpyAsync(stage8, obst + (size_t)r * nx, (size_t)rows * nx, cudaMemcpyHostToDevice, s.stream));
+    rc = stage_in(s, reinterpret_cast<const char *>(obst), (size_t)nx, s.nyl, chunk, [&](char *stage, int r, int rows) {
       const long long threads = (long long)rows * words * 32;
-      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(stage8, s.mask, h->ntx, nx, rows, 1 + r,
-                                                                                  s.free_dev);
+      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(reinterpret_cast<const uint8_t *>(stage), s.mask,
+                                                                                  h->ntx, nx, rows, 1 + r, s.free_dev);
       ++h->launches;
       KERNEL_CHECK(s.stream, "pack_mask");
-      CUDA_TRY(cudaStreamSynchronize(s.stream));
-    }
+      return (int)LBM_OK;
+    });
+    if (rc) return rc;
+  }
+  // all slabs' pipelines were only enqueued above (they overlap across GPUs); wait for them here
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    rc = drain_stages(s);
+    if (rc) return rc;
   }
   return finish_upload(h);
 }
@@ -681,17 +741,21 @@ int lbm_download(lbm_handle *h, float *cells_aos, float *av_vels) {
     for (Slab &s : h->slabs) {
       CUDA_TRY(cudaSetDevice(s.device));
       const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
-      float *cells = cells_aos + first * nx * lbm::kSpeeds;
-      const int rows_per_chunk = (int)std::max<size_t>(1, kStageBytes / ((size_t)nx * lbm::kSpeeds * sizeof(float)));
-      for (int r = 0; r < s.nyl; r += rows_per_chunk) {
-        const int rows = std::min(rows_per_chunk, s.nyl - r);
-        const size_t bytes = (size_t)rows * nx * lbm::kSpeeds * sizeof(float);
-        lbm::tiles_to_aos_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(s.buf[h->cur], s.stage, h->ntx, nx, rows, 1 + r);
-        ++h->launches;
-        KERNEL_CHECK(s.stream, "soa_to_aos");
-        CUDA_TRY(cudaMemcpyAsync(cells + (size_t)r * nx * lbm::kSpeeds, s.stage, bytes, cudaMemcpyDeviceToHost, s.stream));
-        CUDA_TRY(cudaStreamSynchronize(s.stream));
-      }
+      int chunk = 0;
+      int rc = stage_out(s, reinterpret_cast<char *>(cells_aos + first * nx * lbm::kSpeeds), (size_t)nx * lbm::kSpeeds * sizeof(float),
+                         s.nyl, chunk, [&](char *stage, int r, int rows) {
+                           lbm::tiles_to_aos_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
+                               s.buf[h->cur], reinterpret_cast<float *>(stage), h->ntx, nx, rows, 1 + r);
+                           ++h->launches;
+                           KERNEL_CHECK(s.stream, "tiles_to_aos");
+                           return (int)LBM_OK;
+                         });
+      if (rc) return rc;
+    }
+    for (Slab &s : h->slabs) {
+      CUDA_TRY(cudaSetDevice(s.device));
+      int rc = drain_stages(s);
+      if (rc) return rc;
     }
   }
   if (av_vels) {
@@ -710,22 +774,24 @@ int lbm_download_fields(lbm_handle *h, float *fields) {
   if (!h || !fields) return fail(LBM_E_ARG, "null argument");
   if (!h->uploaded) return fail(LBM_E_STATE, "lbm_download_fields before lbm_upload");
   const int nx = h->nx;
-  if ((size_t)nx * 4 * sizeof(float) > kStageBytes)
-    return fail(LBM_E_ARG, "a single row of %d cells does not fit the staging buffer", nx);
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
-    float *out = fields + first * nx * 4;
-    const int rows_per_chunk = (int)std::max<size_t>(1, kStageBytes / ((size_t)nx * 4 * sizeof(float)));
-    for (int r = 0; r < s.nyl; r += rows_per_chunk) {
-      const int rows = std::min(rows_per_chunk, s.nyl - r);
-      lbm::final_state_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(s.buf[h->cur], s.mask, reinterpret_cast<float4 *>(s.stage),
-                                                                          h->ntx, nx, rows, 1 + r, h->density);
-      ++h->launches;
-      KERNEL_CHECK(s.stream, "final_state");
-      CUDA_TRY(cudaMemcpyAsync(out + (size_t)r * nx * 4, s.stage, (size_t)rows * nx * 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-      CUDA_TRY(cudaStreamSynchronize(s.stream));
-    }
+    int chunk = 0;
+    int rc = stage_out(s, reinterpret_cast<char *>(fields + first * nx * 4), (size_t)nx * 4 * sizeof(float), s.nyl, chunk,
+                       [&](char *stage, int r, int rows) {
+                         lbm::final_state_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
+                             s.buf[h->cur], s.mask, reinterpret_cast<float4 *>(stage), h->ntx, nx, rows, 1 + r, h->density);
+                         ++h->launches;
+                         KERNEL_CHECK(s.stream, "final_state");
+                         return (int)LBM_OK;
+                       });
+    if (rc) return rc;
+  }
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    int rc = drain_stages(s);
+    if (rc) return rc;
   }
   return LBM_OK;
 }
@@ -764,6 +830,22 @@ int lbm_rows(lbm_handle *h, int *row_begin, int *row_count) {
     *row_begin = 0;
     *row_count = h->ny;
   }
+  return LBM_OK;
+}
+
+int lbm_slab_count(lbm_handle *h, int *count) {
+  if (!h || !count) return fail(LBM_E_ARG, "null argument");
+  *count = (int)h->slabs.size();
+  return LBM_OK;
+}
+int lbm_slab_info(lbm_handle *h, int slab, int *device, int *row_begin, int *row_count, long long *free_cells) {
+  if (!h) return fail(LBM_E_ARG, "null argument");
+  if (slab < 0 || slab >= (int)h->slabs.size()) return fail(LBM_E_ARG, "slab %d of %zu", slab, h->slabs.size());
+  const Slab &s = h->slabs[slab];
+  if (device) *device = s.device;
+  if (row_begin) *row_begin = s.row0;
+  if (row_count) *row_count = s.nyl;
+  if (free_cells) *free_cells = h->uploaded ? s.free_cells : -1;
   return LBM_OK;
 }
 

@@ -209,6 +209,17 @@ int main(int argc, char *argv[]) {
   if (opt.debug) {
     const double mlups = cell_updates / (device_ms * 1e-3) / 1e6;
     std::cout << "Kernel variant:      \t" << lbm_kernel_variant(engine) << std::endl;
+    int nslabs = 0;
+    lbm_slab_count(engine, &nslabs);
+    for (int i = 0; i < nslabs; ++i) {  // partition diagnostics (cf. main/TileMappingStats.cpp)
+      int dev = 0, r0 = 0, nr = 0;
+      long long free_cells = 0;
+      lbm_slab_info(engine, i, &dev, &r0, &nr, &free_cells);
+      std::cout << "Slab " << i << ":              \tGPU " << dev << ", rows [" << r0 << ", " << r0 + nr << "), " << free_cells
+                << " free cells (" << std::fixed << std::setprecision(2)
+                << 100.0 * static_cast<double>(free_cells) / (static_cast<double>(nr) * static_cast<double>(params->nx)) << " %)" << std::endl;
+      std::cout.unsetf(std::ios::floatfield);
+    }
     std::cout << "Device time:         \t" << std::fixed << std::setprecision(3) << device_ms << " ms" << std::endl;
     std::cout << "Throughput:          \t" << std::setprecision(1) << mlups << " MLUPS, "
               << mlups * 72.0 / 1e3 << " GB/s at 72 B per cell update" << std::endl;

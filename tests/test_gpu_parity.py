@@ -153,6 +153,18 @@ def test_division_and_sqrt_helpers_match_ieee_library(lbm):
     assert r["div9_bad"] == 0 and r["div36_bad"] == 0 and r["sqrt_bad"] == 0 and r["div_bad"] == 0
 
 
+def test_slab_diagnostics(lbm):
+    p = lbm.Params(256, 50, 1, 10, 0.1, 0.005, 1.85)
+    obst = np.zeros((50, 256), np.uint8)
+    obst[:10] = 1
+    with lbm.Solver(p, devices=[0, 0, 0]) as s:
+        assert [d["free_cells"] for d in s.slabs] == [-1, -1, -1]
+        s.upload(lbm.initial_cells(p), obst)
+        info = s.slabs
+    assert [(d["row_begin"], d["row_count"]) for d in info] == [(0, 16), (16, 17), (33, 17)]
+    assert [d["free_cells"] for d in info] == [6 * 256, 17 * 256, 17 * 256] and all(d["device"] == 0 for d in info)
+
+
 def test_errors_are_reported_not_thrown(lbm):
     p = lbm.Params(128, 128, 10, 10, 0.1, 0.005, 1.85)
     with lbm.Solver(p) as s:

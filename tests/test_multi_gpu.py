@@ -65,3 +65,22 @@ def test_one_process_per_gpu_bit_exact(oracle, lbm, tmp_path, nx, ny, world, pie
         assert ulp_distance(z["av_vels"], want_av).max() <= 1
         rows += got.shape[0]
     assert rows == ny
+
+
+def test_lbm_runner_on_two_gpus_writes_the_same_files(lbm, tmp_path):
+    """lbm_runner -n 2 (the reference's --num-ipus flag): same av_vels.dat and final_state.dat as on one GPU (the
+    lattice is bit-identical; av_vels may differ in the last place because the slab partials are added in rank order)."""
+    _need_gpus(lbm, 2)
+    from conftest import obstacles_path, params_path
+    outs = []
+    for n in (1, 2):
+        d = tmp_path / f"n{n}"
+        d.mkdir()
+        r = subprocess.run([lbm.RUNNER_PATH, "--params", params_path("128x256"), "--obstacles", obstacles_path("128x256"), "--outdir",
+                            str(d), "--iters", "3000", "--reruns", "0", "-n", str(n), "-d"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("Slab ") == n
+        outs.append(d)
+    assert (outs[0] / "final_state.dat").read_bytes() == (outs[1] / "final_state.dat").read_bytes()
+    a, b = (np.loadtxt(o / "av_vels.dat", usecols=[1]).astype(np.float32) for o in outs)
+    assert ulp_distance(a, b).max() <= 1
