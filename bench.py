@@ -361,7 +361,7 @@ def main():
             pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "kernel": f"lbm::sweep_kernel<{'true' if variant == 'vec4' else 'false'},{'true' if world > 1 or args.local_slabs > 1 else 'false'}>",
+                "kernel": f"lbm::sweep_kernel<SWEEP_{variant.upper()},{'true' if world > 1 or args.local_slabs > 1 else 'false'}>",
                 "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": cells // world,
                 "avg_launch_ms": round(launch_ms, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
 

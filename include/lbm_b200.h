@@ -95,8 +95,9 @@ int lbm_steps_done(lbm_handle *h, int *steps);
 int lbm_free_cells(lbm_handle *h, long long *count);
 /* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int lbm_launch_count(lbm_handle *h, long long *count);
-/* name of the sweep kernel variant in use: "vec4" (nx % 128 == 0: 128-bit loads and stores) or "scalar"
- * (any nx; LBM_B200_KERNEL=scalar forces it for comparison runs) */
+/* name of the sweep kernel variant in use: "vec4" (nx % 128 == 0: 128-bit loads and stores), "hybrid" (any other
+ * nx > 128: 128-bit path on the full tiles, scalar path on the ragged last tile column) or "scalar" (nx < 128;
+ * LBM_B200_KERNEL=scalar forces it for comparison runs) */
 const char *lbm_kernel_variant(lbm_handle *h);
 
 /* ------------------------------------------------------------------------------------------------

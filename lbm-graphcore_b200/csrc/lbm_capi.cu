@@ -36,7 +36,7 @@ int fail(int code, const char *fmt, ...) {
       return fail(LBM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-enum { KERNEL_SCALAR = 0, KERNEL_VEC4 = 1 };
+enum { KERNEL_SCALAR = lbm::SWEEP_SCALAR, KERNEL_VEC4 = lbm::SWEEP_VEC4, KERNEL_HYBRID = lbm::SWEEP_HYBRID };
 // LBM_B200_DEBUG_SYNC=1: synchronise after every kernel launch and name the kernel that failed
 #define KERNEL_CHECK(stream, name)                                                                      \
   do {                                                                                                   \
@@ -115,7 +115,7 @@ size_t blob_bytes() { return sizeof(cudaIpcMemHandle_t) + 4 * sizeof(int); }
 
 // Choose the sweep kernel and its launch shape for one slab: one CTA of 8 warps per 128 x 8 tile.
 int configure_launch(lbm_handle *h, Slab &s) {
-  s.kernel = (h->nx % lbm::kTileW == 0) ? KERNEL_VEC4 : KERNEL_SCALAR;
+  s.kernel = (h->nx % lbm::kTileW == 0) ? KERNEL_VEC4 : (h->nx > lbm::kTileW ? KERNEL_HYBRID : KERNEL_SCALAR);
   // development knob (parity tests of the scalar path on vectorisable sizes)
   if (const char *e = getenv("LBM_B200_KERNEL"))
     if (!strcmp(e, "scalar")) s.kernel = KERNEL_SCALAR;
@@ -259,11 +259,14 @@ int launch_sweep(lbm_handle *h, Slab &s, bool overlap) {
   const bool pdl = overlap && pdl_enabled;
   cudaError_t e;
   if (s.kernel == KERNEL_VEC4)
-    e = h->multi ? launch_pdl(lbm::sweep_kernel<true, true>, s.grid, s.stream, pdl, a)
-                 : launch_pdl(lbm::sweep_kernel<true, false>, s.grid, s.stream, pdl, a);
+    e = h->multi ? launch_pdl(lbm::sweep_kernel<lbm::SWEEP_VEC4, true>, s.grid, s.stream, pdl, a)
+                 : launch_pdl(lbm::sweep_kernel<lbm::SWEEP_VEC4, false>, s.grid, s.stream, pdl, a);
+  else if (s.kernel == KERNEL_HYBRID)
+    e = h->multi ? launch_pdl(lbm::sweep_kernel<lbm::SWEEP_HYBRID, true>, s.grid, s.stream, pdl, a)
+                 : launch_pdl(lbm::sweep_kernel<lbm::SWEEP_HYBRID, false>, s.grid, s.stream, pdl, a);
   else
-    e = h->multi ? launch_pdl(lbm::sweep_kernel<false, true>, s.grid, s.stream, pdl, a)
-                 : launch_pdl(lbm::sweep_kernel<false, false>, s.grid, s.stream, pdl, a);
+    e = h->multi ? launch_pdl(lbm::sweep_kernel<lbm::SWEEP_SCALAR, true>, s.grid, s.stream, pdl, a)
+                 : launch_pdl(lbm::sweep_kernel<lbm::SWEEP_SCALAR, false>, s.grid, s.stream, pdl, a);
   if (e != cudaSuccess) return fail(LBM_E_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
   ++h->launches;
   KERNEL_CHECK(s.stream, "sweep");
@@ -818,6 +821,7 @@ const char *lbm_kernel_variant(lbm_handle *h) {
   if (!h || h->slabs.empty()) return "";
   switch (h->slabs[0].kernel) {
     case KERNEL_VEC4: return "vec4";
+    case KERNEL_HYBRID: return "hybrid";
     default: return "scalar";
   }
 }

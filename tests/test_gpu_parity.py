@@ -50,13 +50,14 @@ def test_shipped_inputs_bit_exact_short(oracle, lbm, case):
 
 
 @pytest.mark.parametrize("nx,ny", [(100, 37), (3, 2), (1, 1), (31, 5), (257, 3), (130, 64), (129, 6), (255, 7), (127, 14),
-                                   (385, 15), (2, 8), (1, 23)])
-def test_scalar_kernel_ragged_sizes(oracle, lbm, nx, ny):
-    """Sizes the float4 path cannot take (nx % 128 != 0), including the reference KAT shape 3x2 and 1x1; last
+                                   (385, 15), (2, 8), (1, 23), (1000, 30), (640 + 77, 9)])
+def test_ragged_widths_hybrid_and_scalar_kernels(oracle, lbm, nx, ny):
+    """Widths that are not a multiple of the tile (nx % 128 != 0): float4 path on the full tiles + scalar path on the
+    last tile column ("hybrid"), scalar only below 128; including the reference KAT shape 3x2 and 1x1; last
     tile columns with 1, 2 and 127 cells; slab heights that put the north ghost row in a tile of its own."""
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 40, seed=nx * 1000 + ny)
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == "scalar"
+        assert s.kernel_variant == ("hybrid" if nx > 128 else "scalar")
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 40)
 
 

@@ -38,6 +38,7 @@ def case(nx, ny, iters, devices=None, seed=0):
 case(256, 20, 6)
 case(100, 13, 6)
 case(129, 7, 4)
+case(300, 11, 5)
 case(256, 30, 6, devices=[0, 0, 0])
 case(77, 19, 6, devices=[0, 0])
 p = lbm.Params(384, 40, 5, 10, 0.1, 0.005, 1.85)
