@@ -47,6 +47,9 @@ enum { KERNEL_SCALAR = lbm::SWEEP_SCALAR, KERNEL_VEC4 = lbm::SWEEP_VEC4, KERNEL_
 
 constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation
 constexpr size_t kStageBytes = 64u << 20;  // AoS staging chunk for upload/download
+constexpr int kPersistentMaxCtas = 1024;  // upper bound on the persistent kernel's grid
+constexpr size_t kPersistentPartials = 2 * (size_t)kPersistentMaxCtas * lbm::kTileH;
+constexpr size_t kPersistentMaxBytes = 96u << 20;  // both lattices must stay in the 126 MB L2 for the persistent kernel to pay
 
 struct Slab {
   int device = 0;
@@ -69,6 +72,8 @@ struct Slab {
   double *tot_u = nullptr;
   unsigned *ticket = nullptr;      // [0] tile-row ticket, [1..2] edge tickets, [4 ..] per-tile-row CTA tickets
   int *step = nullptr;         // [0] step, [1] error
+  unsigned *barrier = nullptr; // persistent kernel: [0] arrival counter, [1] epoch
+  int persistent_grid = 0;     // > 0: the whole time loop runs as one cooperative launch of this many CTAs
   unsigned long long *free_dev = nullptr;
   float *stage = nullptr;
   // neighbours (own pointers when there is a single slab)
@@ -121,6 +126,24 @@ int configure_launch(lbm_handle *h, Slab &s) {
     if (!strcmp(e, "scalar")) s.kernel = KERNEL_SCALAR;
   s.tiles_y = (s.nyl + 2 + lbm::kTileH - 1) / lbm::kTileH;
   s.grid = h->ntx * s.tiles_y;
+  // Lattices that fit in L2 twice over (the reference's shipped inputs) run their whole time loop as ONE cooperative
+  // launch with a grid barrier per step (sweep_persistent_kernel).  LBM_B200_PERSISTENT=0 disables, =1 forces
+  // (any size, for tests).
+  s.persistent_grid = 0;
+  const int want = getenv("LBM_B200_PERSISTENT") ? atoi(getenv("LBM_B200_PERSISTENT")) : -1;
+  if (!h->multi && want != 0 && (want == 1 || 2 * h->lattice_bytes <= kPersistentMaxBytes)) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    int sms = 0, coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device));
+    if (coop && sms > 0) {
+      // one CTA per SM at most (the barrier costs one atomic per CTA); tile rows are dealt over all their warps
+      const int units = s.grid * lbm::kTileH;
+      int ctas = std::min(std::min(LBM_PERSIST_MINB * sms, kPersistentMaxCtas), units);
+      if (const char *e = getenv("LBM_B200_PERSIST_CTAS")) ctas = std::max(1, std::min(atoi(e), ctas));
+      s.persistent_grid = ctas;
+    }
+  }
   return LBM_OK;
 }
 
@@ -138,7 +161,10 @@ int alloc_slab(lbm_handle *h, Slab &s) {
   const size_t mask_bytes = (size_t)h->tiles_y * h->ntx * lbm::kTileMaskWords * sizeof(uint32_t);
   CUDA_TRY(cudaMalloc((void **)&s.mask, mask_bytes));
   CUDA_TRY(cudaMemset(s.mask, 0, mask_bytes));
-  CUDA_TRY(cudaMalloc((void **)&s.partials, (size_t)h->tiles_y * h->ntx * sizeof(double)));
+  // per-step kernels: one partial per CTA (= tile); persistent kernel: two sets of one partial per warp of its grid
+  CUDA_TRY(cudaMalloc((void **)&s.partials, (kPersistentPartials + (size_t)h->tiles_y * h->ntx) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s.barrier, 2 * sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(s.barrier, 0, 2 * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc((void **)&s.row_partials, (size_t)h->tiles_y * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s.tot_u, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
   CUDA_TRY(cudaMemset(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
@@ -172,6 +198,7 @@ void free_slab(Slab &s) {
   cudaFree(s.step);
   cudaFree(s.ticket);
   cudaFree(s.tot_u);
+  cudaFree(s.barrier);
   cudaFree(s.row_partials);
   cudaFree(s.partials);
   cudaFree(s.mask);
@@ -273,6 +300,29 @@ int launch_sweep(lbm_handle *h, Slab &s, bool overlap) {
   return LBM_OK;
 }
 
+// The whole time loop of a single small slab as one cooperative launch.
+int launch_persistent(lbm_handle *h, Slab &s, int iters) {
+  lbm::SweepArgs a = sweep_args(h, s);
+  float *buf_in = s.buf[h->cur], *buf_out = s.buf[h->cur ^ 1];
+  int t0 = h->steps_done, steps = iters;
+  unsigned *bar = s.barrier;
+  void *args[] = {&a, &buf_in, &buf_out, &t0, &steps, &bar};
+  const void *fn = s.kernel == KERNEL_VEC4     ? (const void *)lbm::sweep_persistent_kernel<lbm::SWEEP_VEC4>
+                   : s.kernel == KERNEL_HYBRID ? (const void *)lbm::sweep_persistent_kernel<lbm::SWEEP_HYBRID>
+                                               : (const void *)lbm::sweep_persistent_kernel<lbm::SWEEP_SCALAR>;
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)s.persistent_grid), dim3(32, lbm::kTileH, 1), args, 0, s.stream);
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+    // the CTAs cannot all be resident here (a shared or partitioned GPU): use one launch per timestep instead
+    cudaGetLastError();
+    s.persistent_grid = 0;
+    return LBM_OK;
+  }
+  if (e != cudaSuccess) return fail(LBM_E_CUDA, "cooperative launch of the persistent sweep failed: %s", cudaGetErrorString(e));
+  ++h->launches;
+  KERNEL_CHECK(s.stream, "sweep_persistent");
+  return LBM_OK;
+}
+
 // ---- staged host <-> device pipelines -------------------------------------------------------------
 // Rows travel in chunks through the two halves of the slab's staging buffer.  `chunk` counts chunks since the last
 // drain so that consecutive pipelines (cells, then obstacles) keep alternating halves correctly.
@@ -360,6 +410,7 @@ int reset_counters(lbm_handle *h) {
     CUDA_TRY(cudaMemsetAsync(s.flags, 0, kFlagBytes, s.stream));
     CUDA_TRY(cudaMemsetAsync(s.ticket, 0, (size_t)(4 + h->tiles_y) * sizeof(unsigned), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.step, 0, 2 * sizeof(int), s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.barrier, 0, 2 * sizeof(unsigned), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.free_dev, 0, sizeof(unsigned long long), s.stream));
   }
@@ -647,6 +698,7 @@ int lbm_run(lbm_handle *h, int iters) {
     CUDA_TRY(cudaSetDevice(s.device));
     CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
   }
+  int iters_left_for_loop = iters;
   if (h->first_run_pending) {
     // accelerate_flow once before step 0 (main/LbmAoS.cpp:352; main/LastChance.cpp:158-183) ...
     const float w1 = h->density * h->accel / 9.f, w2 = h->density * h->accel / 36.f;
@@ -674,12 +726,21 @@ int lbm_run(lbm_handle *h, int iters) {
     h->first_run_pending = false;
   }
   // one launch per slab per timestep, slabs interleaved so no GPU's queue runs ahead of its neighbours
+  if (h->slabs.size() == 1 && h->slabs[0].persistent_grid > 0 && iters > 0) {
+    Slab &s = h->slabs[0];
+    int rc = launch_persistent(h, s, iters);
+    if (rc) return rc;
+    if (s.persistent_grid > 0) {  // (reset to 0 when the cooperative launch was refused: fall through to the loop)
+      h->cur ^= (iters & 1);
+      iters_left_for_loop = 0;
+    }
+  }
   // slabs that share a stream (several slabs on one device) alternate in it, so a sweep is not preceded by a
   // sweep of the same slab: no dependent-launch overlap there (the flag waits need the other slab to finish)
   bool shared_stream = false;
   for (size_t i = 0; i < h->slabs.size(); ++i)
     for (size_t j = 0; j < i; ++j) shared_stream |= (h->slabs[i].stream == h->slabs[j].stream);
-  for (int t = 0; t < iters; ++t) {
+  for (int t = 0; t < iters_left_for_loop; ++t) {
     for (Slab &s : h->slabs) {
       if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
       int rc = launch_sweep(h, s, t > 0 && !shared_stream);
@@ -820,9 +881,9 @@ int lbm_launch_count(lbm_handle *h, long long *count) {
 const char *lbm_kernel_variant(lbm_handle *h) {
   if (!h || h->slabs.empty()) return "";
   switch (h->slabs[0].kernel) {
-    case KERNEL_VEC4: return "vec4";
-    case KERNEL_HYBRID: return "hybrid";
-    default: return "scalar";
+    case KERNEL_VEC4: return h->slabs[0].persistent_grid > 0 ? "vec4-persistent" : "vec4";
+    case KERNEL_HYBRID: return h->slabs[0].persistent_grid > 0 ? "hybrid-persistent" : "hybrid";
+    default: return h->slabs[0].persistent_grid > 0 ? "scalar-persistent" : "scalar";
   }
 }
 int lbm_rows(lbm_handle *h, int *row_begin, int *row_count) {

@@ -45,7 +45,7 @@ def test_shipped_inputs_bit_exact_short(oracle, lbm, case):
     obst = lbm.load_obstacles(p.nx, p.ny, obstacles_path(case))
     assert np.array_equal(obst, oracle.load_obstacles(obstacles_path(case), p.nx, p.ny))
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == "vec4"
+        assert s.kernel_variant == "vec4-persistent"  # fits in L2: the whole time loop is one cooperative launch
     _assert_matches_oracle(oracle, lbm, p, op, lbm.initial_cells(p), obst, 1500)
 
 
@@ -57,7 +57,7 @@ def test_ragged_widths_hybrid_and_scalar_kernels(oracle, lbm, nx, ny):
     tile columns with 1, 2 and 127 cells; slab heights that put the north ghost row in a tile of its own."""
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 40, seed=nx * 1000 + ny)
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == ("hybrid" if nx > 128 else "scalar")
+        assert s.kernel_variant == ("hybrid-persistent" if nx > 128 else "scalar-persistent")
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 40)
 
 
@@ -76,9 +76,29 @@ def test_scalar_kernel_on_vectorisable_sizes(oracle, lbm, nx, ny, monkeypatch):
     monkeypatch.setenv("LBM_B200_KERNEL", "scalar")
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 30, seed=nx * 7 + ny, solid_frac=0.1)
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == "scalar"
+        assert s.kernel_variant == "scalar-persistent"
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30)
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30, devices=[0, 0])
+
+
+@pytest.mark.parametrize("nx,ny", [(256, 64), (1024, 33), (300, 21), (77, 19), (512, 2500)])
+def test_per_step_kernels_on_small_grids(oracle, lbm, nx, ny, monkeypatch):
+    """Small lattices normally take the persistent cooperative kernel; LBM_B200_PERSISTENT=0 sends them through the
+    one-launch-per-step kernels (programmatic dependent launch, single-level reduction) that big grids use."""
+    monkeypatch.setenv("LBM_B200_PERSISTENT", "0")
+    p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 25, seed=nx + 11 * ny, solid_frac=0.07)
+    with lbm.Solver(p) as s:
+        assert "persistent" not in s.kernel_variant
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 25)
+
+
+def test_persistent_kernel_with_several_tiles_per_cta(oracle, lbm, monkeypatch):
+    """LBM_B200_PERSISTENT=1 forces the persistent kernel onto a lattice with more tiles than resident CTAs."""
+    monkeypatch.setenv("LBM_B200_PERSISTENT", "1")
+    p, op, cells, obst = _random_problem(oracle, lbm, 2048, 700, 9, seed=5, solid_frac=0.03)
+    with lbm.Solver(p) as s:
+        assert s.kernel_variant == "vec4-persistent"
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 9)
 
 
 def test_run_in_pieces_equals_one_run(oracle, lbm):
