@@ -117,3 +117,18 @@ def test_baseline_size_properties_and_band_parity(oracle, lbm):
         got = after[lo + a:lo + b]
         assert np.array_equal(got.view(np.uint32), src[a:b].view(np.uint32)), (lo, hi)
         assert hi != ny or np.abs(got[..., 1] - got[..., 3]).max() > 1e-4  # there is flow under the lid
+
+
+def test_lbm_runner_synthetic_channel(lbm, tmp_path):
+    """lbm_runner --synthetic NXxNY generates the channel on the device: same av_vels as the Python binding."""
+    r = subprocess.run([lbm.RUNNER_PATH, "--synthetic", "512x384", "--iters", "60", "--outdir", str(tmp_path), "--reruns", "1", "-d"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MLUPS" in r.stdout and not (tmp_path / "final_state.dat").exists()
+    av = np.loadtxt(tmp_path / "av_vels.dat", usecols=[1]).astype(np.float32)
+    p = lbm.Params(512, 384, 60, 10, 0.1, 0.005, 1.85)
+    with lbm.Solver(p) as s:
+        s.init_synthetic(1234, 0.01)
+        s.run(60)
+        _, want = s.download(cells=False)
+    assert np.array_equal(av.view(np.uint32), want.view(np.uint32))

@@ -174,6 +174,34 @@ def test_division_and_sqrt_helpers_match_ieee_library(lbm):
     assert r["div9_bad"] == 0 and r["div36_bad"] == 0 and r["sqrt_bad"] == 0 and r["div_bad"] == 0
 
 
+@pytest.mark.parametrize("density,accel,omega", [(0.1, 0.0, 1.85), (1.0, 0.01, 0.6), (0.05, 0.002, 1.99), (0.3, 0.02, 1.0)])
+@pytest.mark.parametrize("nx,ny,env", [(256, 24, None), (200, 17, None), (256, 24, "0")])
+def test_other_physical_parameters(oracle, lbm, monkeypatch, density, accel, omega, nx, ny, env):
+    """Relaxation from under- to almost marginally stable over-relaxation, no forcing, strong forcing (the guard of the
+    first accelerate then refuses some cells), other densities: still bit-exact, persistent and per-step kernels."""
+    if env is not None:
+        monkeypatch.setenv("LBM_B200_PERSISTENT", env)
+    rng = np.random.default_rng(int(omega * 100) + nx)
+    p = lbm.Params(nx, ny, 30, 10, density, accel, omega)
+    op = oracle.make_params(nx, ny, 30, 10, density, accel, omega)
+    obst = (rng.random((ny, nx)) < 0.06).astype(np.uint8)
+    cells = (lbm.initial_cells(p) * (1.0 + 0.2 * rng.random((ny, nx, 9))).astype(np.float32)).astype(np.float32)
+    cells[ny - 2, ::7, 3] = 0.0  # f3 - w1 <= 0: the guarded first accelerate must skip these cells
+    _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30)
+
+
+def test_zero_steps_and_download_of_the_initial_state(oracle, lbm):
+    p, op, cells, obst = _random_problem(oracle, lbm, 256, 16, 4, seed=2)
+    with lbm.Solver(p) as s:
+        s.upload(cells, obst)
+        s.run(0)  # applies the one-off accelerate_flow only
+        got, av = s.download()
+        assert s.steps_done == 0 and av.size == 0
+    want = cells.copy()
+    oracle.accelerate_flow(op, want, obst)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_slab_diagnostics(lbm):
     p = lbm.Params(256, 50, 1, 10, 0.1, 0.005, 1.85)
     obst = np.zeros((50, 256), np.uint8)
