@@ -67,10 +67,12 @@ struct Slab {
   int *flags = nullptr;  // [0] from_south, [1] from_north
   // private allocations
   uint32_t *mask = nullptr;
-  double *partials = nullptr;      // [grid] CTA partials
-  double *row_partials = nullptr;  // [tiles_y]
+  double *partials = nullptr;      // [kWindowSteps][grid] CTA partials of the last few timesteps (+ persistent kernel's warp partials)
+  double *row_partials = nullptr;  // [kWindowSteps][tiles_y]
   double *tot_u = nullptr;
-  unsigned *ticket = nullptr;      // [0] tile-row ticket, [1..2] edge tickets, [4 ..] per-tile-row CTA tickets
+  int window_first = 0;            // first timestep whose partials wait in the window
+  int window_count = 0;            // how many
+  unsigned *ticket = nullptr;      // [1..2] edge tickets (multi-slab)
   int *step = nullptr;         // [0] step, [1] error
   unsigned *barrier = nullptr; // persistent kernel: [0] arrival counter, [1] epoch
   int persistent_grid = 0;     // > 0: the whole time loop runs as one cooperative launch of this many CTAs
@@ -161,15 +163,16 @@ int alloc_slab(lbm_handle *h, Slab &s) {
   const size_t mask_bytes = (size_t)h->tiles_y * h->ntx * lbm::kTileMaskWords * sizeof(uint32_t);
   CUDA_TRY(cudaMalloc((void **)&s.mask, mask_bytes));
   CUDA_TRY(cudaMemset(s.mask, 0, mask_bytes));
-  // per-step kernels: one partial per CTA (= tile); persistent kernel: two sets of one partial per warp of its grid
-  CUDA_TRY(cudaMalloc((void **)&s.partials, (kPersistentPartials + (size_t)h->tiles_y * h->ntx) * sizeof(double)));
+  // per-step kernels: kWindowSteps slots of one partial per CTA (= tile); persistent kernel: two sets of one partial per warp
+  CUDA_TRY(cudaMalloc((void **)&s.partials,
+                      std::max(kPersistentPartials, (size_t)lbm::kWindowSteps * h->tiles_y * h->ntx) * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s.barrier, 2 * sizeof(unsigned)));
   CUDA_TRY(cudaMemset(s.barrier, 0, 2 * sizeof(unsigned)));
-  CUDA_TRY(cudaMalloc((void **)&s.row_partials, (size_t)h->tiles_y * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s.row_partials, (size_t)lbm::kWindowSteps * h->tiles_y * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s.tot_u, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
   CUDA_TRY(cudaMemset(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&s.ticket, (size_t)(4 + h->tiles_y) * sizeof(unsigned)));
-  CUDA_TRY(cudaMemset(s.ticket, 0, (size_t)(4 + h->tiles_y) * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc((void **)&s.ticket, 4 * sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(s.ticket, 0, 4 * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc((void **)&s.step, 2 * sizeof(int)));
   CUDA_TRY(cudaMemset(s.step, 0, 2 * sizeof(int)));
   CUDA_TRY(cudaMalloc((void **)&s.free_dev, sizeof(unsigned long long)));
@@ -248,13 +251,10 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   a.one_minus_omega = 1 - h->omega;                 // main/LastChance.cpp:387
   a.w1 = h->density * h->accel / 9.f;               // main/LastChance.cpp:158
   a.w2 = h->density * h->accel / 36.f;              // :159
+  a.t = h->steps_done;  // launch_sweep overrides it for every step of a run
   a.partials = s.partials;
-  a.row_partials = s.row_partials;
   a.tot_u = s.tot_u;
-  a.ticket = s.ticket;
   a.edge_ticket = s.ticket + 1;
-  a.row_ticket = s.ticket + 4;
-  a.step = s.step;
   a.flag_from_south = s.flags + 0;
   a.flag_from_north = s.flags + 1;
   a.flag_to_south = s.flag_to_south;
@@ -280,9 +280,31 @@ cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, bool pdl, const 
 
 // One timestep of one slab.  `overlap` = this launch directly follows another sweep of the same slab in the
 // stream, so it may be scheduled while that one drains (programmatic dependent launch; LBM_B200_PDL=0 disables).
-int launch_sweep(lbm_handle *h, Slab &s, bool overlap) {
+// Finish the sums of the timesteps whose CTA partials wait in the slab's window: tot_u[window_first ...].
+int flush_reductions(lbm_handle *h, Slab &s) {
+  if (s.window_count == 0) return LBM_OK;
+  lbm::reduce_rows_kernel<<<dim3((unsigned)s.tiles_y, (unsigned)s.window_count), 256, 0, s.stream>>>(s.partials, s.row_partials, h->ntx,
+                                                                                                 s.tiles_y);
+  lbm::reduce_total_kernel<<<(unsigned)s.window_count, 256, 0, s.stream>>>(s.row_partials, s.tot_u + s.window_first, s.tiles_y);
+  h->launches += 2;
+  KERNEL_CHECK(s.stream, "reduce_rows/reduce_total");
+  s.window_first += s.window_count;
+  s.window_count = 0;
+  return LBM_OK;
+}
+
+int launch_sweep(lbm_handle *h, Slab &s, int t, bool overlap) {
   static const bool pdl_enabled = !(getenv("LBM_B200_PDL") && atoi(getenv("LBM_B200_PDL")) == 0);
-  const lbm::SweepArgs a = sweep_args(h, s);
+  if (s.window_count == lbm::kWindowSteps) {
+    int rc = flush_reductions(h, s);
+    if (rc) return rc;
+    overlap = false;  // the reduce kernels now sit between the two sweeps
+  }
+  if (s.window_count == 0) s.window_first = t;
+  lbm::SweepArgs a = sweep_args(h, s);
+  a.t = t;
+  a.partials = s.partials + (size_t)s.window_count * s.grid;
+  ++s.window_count;
   const bool pdl = overlap && pdl_enabled;
   cudaError_t e;
   if (s.kernel == KERNEL_VEC4)
@@ -408,7 +430,9 @@ int reset_counters(lbm_handle *h) {
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     CUDA_TRY(cudaMemsetAsync(s.flags, 0, kFlagBytes, s.stream));
-    CUDA_TRY(cudaMemsetAsync(s.ticket, 0, (size_t)(4 + h->tiles_y) * sizeof(unsigned), s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.ticket, 0, 4 * sizeof(unsigned), s.stream));
+    s.window_first = 0;
+    s.window_count = 0;
     CUDA_TRY(cudaMemsetAsync(s.step, 0, 2 * sizeof(int), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.barrier, 0, 2 * sizeof(unsigned), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double), s.stream));
@@ -743,10 +767,15 @@ int lbm_run(lbm_handle *h, int iters) {
   for (int t = 0; t < iters_left_for_loop; ++t) {
     for (Slab &s : h->slabs) {
       if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
-      int rc = launch_sweep(h, s, t > 0 && !shared_stream);
+      int rc = launch_sweep(h, s, h->steps_done + t, t > 0 && !shared_stream);
       if (rc) return rc;
     }
     h->cur ^= 1;
+  }
+  for (Slab &s : h->slabs) {
+    if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
+    int rc = flush_reductions(h, s);
+    if (rc) return rc;
   }
   h->steps_done += iters;
   for (Slab &s : h->slabs) {
