@@ -73,7 +73,7 @@ struct Slab {
   int window_first = 0;            // first timestep whose partials wait in the window
   int window_count = 0;            // how many
   unsigned *ticket = nullptr;      // [1..2] edge tickets (multi-slab)
-  int *step = nullptr;         // [0] step, [1] error
+  int *step = nullptr;         // [1] error flag set by a kernel that gave up waiting ([0] unused)
   unsigned *barrier = nullptr; // persistent kernel: [0] arrival counter, [1] epoch
   int persistent_grid = 0;     // > 0: the whole time loop runs as one cooperative launch of this many CTAs
   unsigned long long *free_dev = nullptr;
