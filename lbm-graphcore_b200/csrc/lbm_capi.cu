@@ -74,7 +74,7 @@ struct Slab {
   int window_count = 0;            // how many
   unsigned *ticket = nullptr;      // [1..2] edge tickets (multi-slab)
   int *step = nullptr;         // [1] error flag set by a kernel that gave up waiting ([0] unused)
-  unsigned *barrier = nullptr; // persistent kernel: [0] arrival counter, [1] epoch
+  unsigned long long *barrier = nullptr;  // persistent kernel: grid-barrier arrivals since the last upload
   int persistent_grid = 0;     // > 0: the whole time loop runs as one cooperative launch of this many CTAs
   unsigned long long *free_dev = nullptr;
   float *stage = nullptr;
@@ -166,8 +166,8 @@ int alloc_slab(lbm_handle *h, Slab &s) {
   // per-step kernels: kWindowSteps slots of one partial per CTA (= tile); persistent kernel: two sets of one partial per warp
   CUDA_TRY(cudaMalloc((void **)&s.partials,
                       std::max(kPersistentPartials, (size_t)lbm::kWindowSteps * h->tiles_y * h->ntx) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&s.barrier, 2 * sizeof(unsigned)));
-  CUDA_TRY(cudaMemset(s.barrier, 0, 2 * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc((void **)&s.barrier, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(s.barrier, 0, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc((void **)&s.row_partials, (size_t)lbm::kWindowSteps * h->tiles_y * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s.tot_u, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
   CUDA_TRY(cudaMemset(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
@@ -327,7 +327,7 @@ int launch_persistent(lbm_handle *h, Slab &s, int iters) {
   lbm::SweepArgs a = sweep_args(h, s);
   float *buf_in = s.buf[h->cur], *buf_out = s.buf[h->cur ^ 1];
   int t0 = h->steps_done, steps = iters;
-  unsigned *bar = s.barrier;
+  unsigned long long *bar = s.barrier;
   void *args[] = {&a, &buf_in, &buf_out, &t0, &steps, &bar};
   const void *fn = s.kernel == KERNEL_VEC4     ? (const void *)lbm::sweep_persistent_kernel<lbm::SWEEP_VEC4>
                    : s.kernel == KERNEL_HYBRID ? (const void *)lbm::sweep_persistent_kernel<lbm::SWEEP_HYBRID>
@@ -434,7 +434,7 @@ int reset_counters(lbm_handle *h) {
     s.window_first = 0;
     s.window_count = 0;
     CUDA_TRY(cudaMemsetAsync(s.step, 0, 2 * sizeof(int), s.stream));
-    CUDA_TRY(cudaMemsetAsync(s.barrier, 0, 2 * sizeof(unsigned), s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.barrier, 0, sizeof(unsigned long long), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.free_dev, 0, sizeof(unsigned long long), s.stream));
   }
