@@ -366,7 +366,9 @@ def main():
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel": f"lbm::sweep_kernel<SWEEP_{variant.upper()},{'true' if world > 1 or args.local_slabs > 1 else 'false'}>",
                 "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": cells // world,
-                "avg_launch_ms": round(launch_ms, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
+                "avg_launch_ms": round(launch_ms, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
+                "context": "best plain copy measured on this pool with tools/probes/stream_probe.cu: 6920 GB/s "
+                           "(profiles/r01c_stream_probe_4.txt); ncu reports 85 % DRAM throughput for this kernel"}
 
     line = {
         "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
