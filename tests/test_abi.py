@@ -91,3 +91,33 @@ def test_product_never_touches_the_oracle():
     assert not offenders, offenders
     ldd = subprocess.run(["ldd", os.path.join(pkg, "liblbm_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in ldd and "torch" not in ldd
+
+
+def test_runner_cli_errors_before_any_gpu_work(lbm, tmp_path):
+    """Flag handling of the LbmRunner-style driver (main/LbmRunner.cpp:16-48): both input files are mandatory, unknown
+    flags print the usage, unreadable or malformed inputs abort with the reference's messages -- all before CUDA."""
+    run = lambda *a: subprocess.run([lbm.RUNNER_PATH, *a], capture_output=True, text=True)
+    gold = os.path.join(ROOT, "tests", "golden", "params")
+    r = run()
+    assert r.returncode != 0 and "--params" in r.stderr and "--obstacles" in r.stderr
+    r = run("--params", os.path.join(gold, "input_128x128.params"))
+    assert r.returncode != 0 and "--obstacles" in r.stderr
+    r = run("--bogus")
+    assert r.returncode != 0 and "Runs a Lattice Boltzmann simulation" in r.stderr
+    r = run("--params", str(tmp_path / "nope.params"), "--obstacles", os.path.join(gold, "obstacles_128x128.dat"))
+    assert r.returncode != 0 and "Could not parse parameters file" in r.stderr
+    bad = tmp_path / "bad.params"
+    bad.write_text("128\n128\n")
+    r = run("--params", str(bad), "--obstacles", os.path.join(gold, "obstacles_128x128.dat"))
+    assert r.returncode != 0 and "Could not parse parameters file" in r.stderr
+    r = run("--params", os.path.join(gold, "input_128x128.params"), "--obstacles", str(tmp_path / "nope.dat"))
+    assert r.returncode != 0 and "Could not parse obstacles file" in r.stderr
+    r = run("--synthetic", "128x", "--iters", "5")
+    assert r.returncode != 0
+    # the reference's flag spellings are accepted: --num-ipus, --device, --exe (the last two ignored)
+    r = run("--params=" + os.path.join(gold, "input_128x128.params"), "--obstacles=" + os.path.join(gold, "obstacles_128x128.dat"),
+            "--num-ipus", "1", "--device", "ipu", "--exe", "graph.exe", "--outdir", str(tmp_path), "--reruns", "0")
+    if lbm.device_count() == 0:
+        assert r.returncode != 0 and "no CPU path" in r.stderr
+    else:
+        assert r.returncode == 0 and "==done==" in r.stdout
