@@ -19,11 +19,21 @@ One JSON line on stdout (rank 0):
   roofline    achieved = 72 B/cell * cells per launch / average launch time, against the measured copy
               bandwidth in MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (a port of the reference's main/LastChance.cpp loop, OpenMP over rows)
-              timed on this box's host cores on a bounded sample
+              timed on this box's host cores on a bounded sample (N = 1 only)
+  parity      (outside the timed region) a perturbed random problem run on the N GPUs of this launch, compared
+              with the same problem as one slab on rank 0's GPU and with the CPU oracle: lattice SHA-256 per
+              rank, av_vels in ulps.  A mismatch makes the run exit non-zero.
+  weak        BASELINE.json configs[4] -- 32768 x 32768 cells PER GPU -- measured in the same launch
+  shipped     (N = 1) BASELINE.json configs[0-2]: the reference's 128^2 / 256^2 / 1024^2 inputs for their full
+              maxIters, microseconds per step, MLUPS, check.py's verdict and the lattice hash against the oracle
+  detail      free-form facts about this run (partition, kernel variant, last av_vels, wall clock per step)
+The reference arm times the oracle port (OpenMP over rows, all host cores) on the SAME grid for W + K real timesteps.
 Under torchrun (N > 1) every rank runs this file; rank r drives GPU LOCAL_RANK.
 """
 import argparse
 import ctypes
+import gzip
+import hashlib
 import importlib
 import json
 import os
@@ -40,6 +50,7 @@ sys.path.insert(0, ROOT)
 BYTES_PER_CELL = 72  # 9 fp32 read + 9 fp32 written per lattice update
 DENSITY, ACCEL, OMEGA, REYNOLDS_DIM = 0.1, 0.005, 1.85, 10
 SEED, SOLID_PROB = 1234, 0.01
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def parse_args():
@@ -55,6 +66,9 @@ def parse_args():
                     help="development only: cut the grid into this many row slabs that all live on GPU 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--no-shipped", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU time budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -71,6 +85,18 @@ def grid_for(args, world):
     if args.nx or args.ny:
         name = f"synthetic channel {nx}x{ny} (override)"
     return nx, ny, scaling, name
+
+
+def workload_config(name, nx, ny):
+    """The `config` object: the workload only, so that both arms print the same one."""
+    lattice_gb = nx * ny * 36 / 1e9
+    if nx * ny * 72 > 8 * 4 * 126e6:
+        l2 = (f"working set (2 lattices of {lattice_gb:.2f} GB, split evenly over the GPUs of the run) >> 126 MB L2 per "
+              "GPU: no flush needed between steps")
+    else:
+        l2 = "development override: the lattices fit in L2 (latency-bound small grid, not the benchmark)"
+    return {"workload": name, "nx": nx, "ny": ny, "density": DENSITY, "accel": ACCEL, "omega": OMEGA, "seed": SEED,
+            "solid_prob": SOLID_PROB, "l2": l2}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -128,23 +154,48 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port (OpenMP over rows) on a bounded sample of the same workload
+# CPU side: the oracle port (OpenMP over rows).  cpu_baseline = a bounded band of the workload (our arm's reported
+# baseline); the reference arm = the whole grid for W + K real timesteps.
 # ---------------------------------------------------------------------------------------------------
-def cpu_baseline(nx, ny, budget_s, lbm_mod):
-    from oracle import oracle
-
-    cores = os.cpu_count() or 1
+def host_cores():
     try:
-        cores = len(os.sched_getaffinity(0))
+        return len(os.sched_getaffinity(0))
     except AttributeError:
-        pass
-    # same generator and parameters; a full-width horizontal band keeps the sample's memory bounded
-    rows = min(ny, 2048)
+        return os.cpu_count() or 1
+
+
+def load_problem_module():
+    """lbm-graphcore_b200/problem.py on its own (pure numpy): the reference arm loads none of the CUDA product."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("lbm_problem", os.path.join(ROOT, "lbm-graphcore_b200", "problem.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["lbm_problem"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+ORACLE_BUILD = ("oracle/lbm_oracle.c = main/LastChance.cpp:185-267 restated, gcc -O3 -march=x86-64-v3 -ffp-contract=off, "
+                "OpenMP over rows, fp64 tot_u")
+
+
+def cpu_channel(nx, ny, rows, problem_mod):
+    """Initial state of the first `rows` rows of the nx x ny synthetic channel (all of it when rows == ny)."""
+    from oracle import oracle
     op = oracle.make_params(nx, rows, 1, REYNOLDS_DIM, DENSITY, ACCEL, OMEGA)
-    obst = lbm_mod.synthetic_obstacles(nx, rows, SEED, SOLID_PROB)
+    obst = np.empty((rows, nx), dtype=np.uint8)
+    for r in range(0, rows, 1024):
+        n = min(1024, rows - r)
+        obst[r:r + n] = problem_mod.synthetic_obstacles(nx, ny if rows == ny else rows, SEED, SOLID_PROB, r, n)
     a = oracle.init_cells(op)
     b = np.empty_like(a)
     oracle.accelerate_flow(op, a, obst)
+    return oracle, op, obst, a, b
+
+
+def cpu_baseline(nx, ny, budget_s, problem_mod):
+    cores = host_cores()
+    rows = min(ny, 2048)  # a full-width horizontal band keeps the sample's memory and time bounded
+    oracle, op, obst, a, b = cpu_channel(nx, ny, rows, problem_mod)
     oracle.timestep_rows(op, a, b, obst, 0, rows, oracle.ACCUM_DOUBLE, cores)  # warm-up / page faults
     a, b = b, a
     t0 = time.perf_counter()
@@ -158,9 +209,7 @@ def cpu_baseline(nx, ny, budget_s, lbm_mod):
             break
     mlups = nx * rows * steps / dt / 1e6
     return {"value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": "port",
-            "sample": f"{steps} timesteps of a {nx}x{rows} band of the same synthetic channel "
-                      f"(oracle/lbm_oracle.c = main/LastChance.cpp:185-267 restated, gcc -O3 -march=x86-64-v3 "
-                      f"-ffp-contract=off, OpenMP over rows, fp64 tot_u), {dt:.1f} s"}
+            "sample": f"{steps} timesteps of a {nx}x{rows} band of the same synthetic channel ({ORACLE_BUILD}), {dt:.1f} s"}
 
 
 def reference_program_baseline():
@@ -168,7 +217,7 @@ def reference_program_baseline():
     own flags, -O3 and FMA contraction allowed) on the reference's own CPU-runnable case, BASELINE.json configs[0]:
     input_128x128, 40 000 timesteps, single-threaded as shipped.  None when oracle/_ref was never built."""
     exe = os.path.join(ROOT, "oracle", "_ref", "compareLbm_fma")
-    gold = os.path.join(ROOT, "tests", "golden", "params")
+    gold = os.path.join(GOLDEN, "params")
     if not os.path.exists(exe):
         return None
     with tempfile.TemporaryDirectory() as tmp:
@@ -183,34 +232,202 @@ def reference_program_baseline():
                       f"incl. its file output, {dt:.1f} s wall"}
 
 
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return None
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores.  The unmodified
-    program (oracle/_ref/compareLbm_*) always writes final_state.dat (25 GB of text at 16384^2) and is
-    single-threaded, so the headline grid is timed with the oracle port of the same loop on all cores."""
+    """--impl reference: the reference's CPU implementation of the path (main/LastChance.cpp:185-267, restated in
+    oracle/lbm_oracle.c) on all host cores, on the SAME grid as our arm, for W untimed + K timed real timesteps.
+    The unmodified program (oracle/_ref/compareLbm_*) is single-threaded and always writes final_state.dat (25 GB of text
+    at 16384^2), so the headline grid is timed with the port of the same loop; the unmodified program's own timing on
+    its 128x128 case rides along as cpu_baseline.reference_program."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # only the pure-numpy problem generator is shared with our arm; none of the CUDA product is loaded here
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("lbm_problem", os.path.join(ROOT, "lbm-graphcore_b200", "problem.py"))
-    lbm_mod = importlib.util.module_from_spec(spec)
-    sys.modules["lbm_problem"] = lbm_mod
-    spec.loader.exec_module(lbm_mod)
+    problem_mod = load_problem_module()
     nx, ny, scaling, name = grid_for(args, max(args.gpus, 1))
-    # budget: K+W "steps" of a bounded band, a few minutes at most
-    base = cpu_baseline(nx, ny, min(120.0, max(10.0, 0.5 * (args.steps + args.warmup))), lbm_mod)
+    K, W = args.steps, args.warmup
+    cores = host_cores()
+    need = nx * ny * (2 * 36 + 1) * 1.05
+    avail = mem_available_bytes()
+    rows = ny
+    if avail is not None and need > 0.9 * avail:  # a host too small for the whole grid: the tallest band that fits
+        rows = max(64, int(ny * 0.9 * avail / need) // 64 * 64)
+    oracle, op, obst, a, b = cpu_channel(nx, ny, rows, problem_mod)
+    tot = []
+    for _ in range(W):
+        oracle.timestep_rows(op, a, b, obst, 0, rows, oracle.ACCUM_DOUBLE, cores)
+        a, b = b, a
+    t0 = time.perf_counter()
+    for _ in range(K):
+        tot.append(oracle.timestep_rows(op, a, b, obst, 0, rows, oracle.ACCUM_DOUBLE, cores))
+        a, b = b, a
+    dt = time.perf_counter() - t0
+    if not np.all(np.isfinite(tot)):
+        raise SystemExit("bench.py: the reference arm produced a non-finite av_vels")
+    mlups = nx * rows * K / dt / 1e6
+    whole = rows == ny
+    sample = (f"{W} + {K} timesteps of the whole {nx}x{ny} grid" if whole else
+              f"{W} + {K} timesteps of a {nx}x{rows} band (the host has {avail / 1e9:.0f} GB free; the whole grid needs "
+              f"{need / 1e9:.0f} GB)") + f" ({ORACLE_BUILD}), {dt:.1f} s timed"
+    base = {"value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample}
+    ref = reference_program_baseline() if not (args.nx or args.ny) else None
+    if ref is not None:
+        base["reference_program"] = ref
     line = {
         "impl": "reference", "metric": "MLUPS", "value": base["value"], "unit": "MLUPS", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(nx * ny / (base["value"] * 1e6) * 1e3, 3), "higher_is_better": True,
+        "steps": K, "warmup": W, "ms_per_step": round(dt * 1e3 / K * (ny / rows), 3), "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "nx": nx, "ny": ny, "density": DENSITY, "accel": ACCEL, "omega": OMEGA, "seed": SEED,
-                   "solid_prob": SOLID_PROB},
+        "config": workload_config(name, nx, ny),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "detail": {"rows_timed": rows, "timed_s": round(dt, 6), "tot_u_last": float(tot[-1]) if tot else None},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# driver-visible correctness and the other BASELINE.json configurations (all outside the timed region)
+# ---------------------------------------------------------------------------------------------------
+def ulp_distance(a, b):
+    ai = np.ascontiguousarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    bi = np.ascontiguousarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    return int(np.abs(ai - bi).max()) if ai.size else 0
+
+
+def parity_record(lbm, slabs, dist, rank, world, local_rank):
+    """A problem whose halo rows matter from the first step (5 % random solids, every population perturbed) on the N
+    GPUs of this launch -- one rank per GPU, halo rows stored into the neighbour's memory by the sweep kernel -- against
+    (a) the same problem as ONE slab on rank 0's GPU and (b) the CPU oracle (the checker, never the thing measured).
+    With one GPU the multi-slab kernel is exercised by two slabs that share the GPU."""
+    nx, ny, iters, seed = 2048, 96 * max(world, 2), 40, 4242
+    p, cells, obst = lbm.perturbed_problem(nx, ny, iters, seed)
+    if world > 1:
+        s = lbm.Solver(p, rank=rank, world=world, device=local_rank)
+        slabs.connect_ring(s, dist)
+        r0, n = s.row_begin, s.row_count
+        s.upload(cells[r0:r0 + n], obst[r0:r0 + n])
+        dist.barrier()
+        s.run(iters)
+        got, _ = s.download(av_vels=False)
+        av = slabs.combine_av_vels(dist, s.download_tot_u(), s.free_cells)
+        variant = s.kernel_variant
+        slabs.close_ring(s, dist)
+        mine = (r0, n, hashlib.sha256(got.tobytes()).hexdigest())
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    else:
+        with lbm.Solver(p, devices=[0, 0]) as s:
+            s.upload(cells, obst)
+            s.run(iters)
+            got, av = s.download()
+            variant = s.kernel_variant
+            parts = [(sl["row_begin"], sl["row_count"],
+                      hashlib.sha256(got[sl["row_begin"]:sl["row_begin"] + sl["row_count"]].tobytes()).hexdigest())
+                     for sl in s.slabs]
+    if rank != 0:
+        return None
+    from oracle import oracle
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE, threads=host_cores())
+    halo_equal = all(hashlib.sha256(want[r0:r0 + n].tobytes()).hexdigest() == h for r0, n, h in parts)
+    with lbm.Solver(p, num_gpus=1) as s1:
+        s1.upload(cells, obst)
+        s1.run(iters)
+        one, one_av = s1.download()
+    rec = {"problem": f"perturbed {nx}x{ny}, 5 % random solids, {iters} steps, seed {seed}",
+           "partition": f"{world} rank(s), one row slab per GPU" if world > 1 else "2 row slabs sharing the one GPU",
+           "kernel_variant": variant,
+           "halo_lattice_sha_equal": bool(halo_equal),
+           "one_slab_lattice_sha_equal": hashlib.sha256(one.tobytes()).hexdigest() == hashlib.sha256(want.tobytes()).hexdigest(),
+           "lattice_sha256": hashlib.sha256(want.tobytes()).hexdigest()[:16],
+           "av_vels_max_ulp": ulp_distance(av, want_av), "one_slab_av_vels_max_ulp": ulp_distance(one_av, want_av),
+           "vs": "oracle"}
+    rec["ok"] = bool(rec["halo_lattice_sha_equal"] and rec["one_slab_lattice_sha_equal"] and rec["av_vels_max_ulp"] <= 1 and
+                     rec["one_slab_av_vels_max_ulp"] <= 1)
+    return rec
+
+
+def shipped_records(lbm):
+    """BASELINE.json configs[0-2]: the reference's shipped inputs for their full maxIters on one B200, validated the way
+    the reference validates itself (check/check.py:84-100,134-147: av_vels and final-state pressure within 1 % of its
+    goldens; 256^2 and 1024^2 ship no final_state golden, there the oracle fixture's pressure field stands in) and,
+    more strictly, by the SHA-256 of the final lattice against the oracle fixture."""
+    from tools import check as check_tool
+    out = []
+    for case in ("128x128", "256x256", "1024x1024"):
+        pfile = os.path.join(GOLDEN, "params", f"input_{case}.params")
+        p = lbm.Params.from_file(pfile)
+        obst = lbm.load_obstacles(p.nx, p.ny, os.path.join(GOLDEN, "params", f"obstacles_{case}.dat"))
+        fx = np.load(os.path.join(GOLDEN, f"oracle_{case}.npz"))
+        with lbm.Solver(p) as s:
+            s.upload(lbm.initial_cells(p), obst)
+            s.run(p.max_iters)
+            ms = s.elapsed_ms
+            cells, av = s.download()
+            fields = s.download_fields()
+            variant = s.kernel_variant
+        with gzip.open(os.path.join(GOLDEN, "check", f"{case}.av_vels.dat.gz"), "rt") as f:
+            av_ref = np.loadtxt(f, usecols=[1])
+        d_av = check_tool.get_diff_values(av_ref, av.astype(np.float64))
+        ok = bool(np.isfinite(d_av["max_diff_pcnt"]) and abs(d_av["max_diff_pcnt"]) <= 1.0)
+        fs_path = os.path.join(GOLDEN, "check", f"{case}.final_state.dat.gz")
+        if os.path.exists(fs_path):
+            with gzip.open(fs_path, "rt") as f:
+                p_ref = np.loadtxt(f, usecols=[5])
+            p_src = "reference golden check/%s.final_state.dat" % case
+            p_sim = fields[..., 3].astype(np.float64).reshape(-1)
+        else:
+            st = int(fx["stride"])
+            p_ref = fx["pressure"].astype(np.float64).reshape(-1)
+            p_src = "oracle fixture (the reference ships no final_state golden for this size)"
+            p_sim = fields[::st, ::st, 3].astype(np.float64).reshape(-1)
+        d_fs = check_tool.get_diff_values(p_ref, p_sim)
+        ok = ok and bool(np.isfinite(d_fs["max_diff_pcnt"]) and abs(d_fs["max_diff_pcnt"]) <= 1.0)
+        sha_ok = hashlib.sha256(cells.tobytes()).hexdigest() == str(fx["cells_sha256"])
+        out.append({"config": f"params/input_{case}.params + obstacles_{case}.dat", "steps": p.max_iters,
+                    "us_per_step": round(ms * 1e3 / p.max_iters, 3),
+                    "mlups": round(p.nx * p.ny * p.max_iters / (ms * 1e-3) / 1e6, 1), "device_s": round(ms / 1e3, 4),
+                    "kernel_variant": variant, "check_py": "pass" if ok else "FAIL",
+                    "av_vels_max_diff_pcnt": float(abs(d_av["max_diff_pcnt"])),
+                    "pressure_max_diff_pcnt": float(abs(d_fs["max_diff_pcnt"])), "pressure_reference": p_src,
+                    "lattice_sha256_equals_oracle": bool(sha_ok),
+                    "av_vels_max_ulp_vs_oracle": ulp_distance(av, fx["av_f64sum"])})
+    return out
+
+
+def weak_record(lbm, slabs, dist, rank, world, local_rank, peak, max_over_ranks):
+    """BASELINE.json configs[4]: 32768 x 32768 cells per GPU (77 GB of lattices each), row slabs, weak scaling."""
+    nx, nyl, K, W = 32768, 32768, 10, 3
+    p = lbm.Params(nx, nyl * world, W + K, REYNOLDS_DIM, DENSITY, ACCEL, OMEGA)
+    if world == 1:
+        s = lbm.Solver(p, num_gpus=1)
+    else:
+        s = lbm.Solver(p, rank=rank, world=world, device=local_rank)
+        slabs.connect_ring(s, dist)
+    s.init_synthetic(SEED, SOLID_PROB)
+    if dist is not None:
+        dist.barrier()
+    s.run(W)
+    if dist is not None:
+        dist.barrier()
+    s.run(K)
+    ms = max_over_ranks(s.elapsed_ms)
+    av_last = float(slabs.combine_av_vels(dist, s.download_tot_u(), s.free_cells)[-1])
+    slabs.close_ring(s, dist)
+    mlups = nx * nyl * world * K / (ms * 1e-3) / 1e6
+    gbs = nx * nyl * BYTES_PER_CELL / (ms / K * 1e-3) / 1e9
+    return {"workload": "synthetic channel 32768x32768 per GPU (BASELINE.json configs[4])", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": round(ms / K, 4), "mlups": round(mlups, 1), "per_gpu_gbs": round(gbs, 1),
+            "frac_of_measured_peak": round(gbs / peak, 4), "av_vels_last": av_last, "finite": bool(np.isfinite(av_last))}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -291,7 +508,7 @@ def main():
     cells = nx * ny
     mlups = cells * K / (ms * 1e-3) / 1e6
     variant = solver.kernel_variant
-    solver.close()
+    slabs.close_ring(solver, dist)
 
     # ---- end-to-end through host buffers -------------------------------------------------------
     e2e = None
@@ -300,8 +517,8 @@ def main():
         p2 = lbm.Params(nx, ny, K, REYNOLDS_DIM, DENSITY, ACCEL, OMEGA)
         nbytes_cells = rows * nx * 9 * 4
         nbytes_obst = rows * nx
-        hc = lbm.lib.lbm_host_alloc(nbytes_cells)
-        ho = lbm.lib.lbm_host_alloc(nbytes_obst)
+        hc = lbm.host_alloc(nbytes_cells, local_rank)
+        ho = lbm.host_alloc(nbytes_obst, local_rank)
         if not hc or not ho:
             raise SystemExit("bench.py: pinned host allocation failed")
         cells_h = np.ctypeslib.as_array(ctypes.cast(hc, ctypes.POINTER(ctypes.c_float)), shape=(rows, nx, 9))
@@ -321,24 +538,46 @@ def main():
         barrier()
         t0 = time.perf_counter()
         s2.upload_raw(hc, ho)
-        barrier()  # every rank's lattice is in place before anyone pushes halo rows
+        t_up = time.perf_counter() - t0
+        barrier()  # every rank's lattice is in place before anyone pushes halo rows (protocol of include/lbm_b200.h)
         s2.run(K)
+        t1 = time.perf_counter()
         if world == 1:
             s2.download_raw(hc, av_h.ctypes.data)
         else:
             s2.download_raw(hc, None)
             part = s2.download_tot_u()
+        t_down = time.perf_counter() - t1
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        t_up, t_down = max_over_ranks(t_up), max_over_ranks(t_down)
         if world == 1 and not np.isfinite(av_h[-1]):
             raise SystemExit("bench.py: e2e av_vels is not finite")
         e2e = {"value": round(cells * K / dt / 1e6, 1), "unit": "MLUPS",
                "h2d_bytes_per_step": int((nbytes_cells + nbytes_obst) * world / K),
                "d2h_bytes_per_step": int((nbytes_cells * world + 8 * K) / K),
-               "job": f"lbm_upload + lbm_run({K}) + lbm_download, pinned host AoS buffers, {dt:.3f} s wall"}
-        s2.close()
+               "job": f"lbm_upload + lbm_run({K}) + lbm_download, pinned host AoS buffers, {dt:.3f} s wall",
+               "upload_s": round(t_up, 4), "download_s": round(t_down, 4),
+               "h2d_gbs_per_gpu": round((nbytes_cells + nbytes_obst) / t_up / 1e9, 1),
+               "d2h_gbs_per_gpu": round(nbytes_cells / t_down / 1e9, 1)}
+        slabs.close_ring(s2, dist)
         lbm.lib.lbm_host_free(hc)
         lbm.lib.lbm_host_free(ho)
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- driver-visible parity, weak scaling and the shipped inputs (outside the timed region) ----
+    parity = None if args.no_parity else parity_record(lbm, slabs, dist, rank, world, local_rank)
+    weak = None
+    if not args.no_weak and args.workload != "weak32768" and not (args.nx or args.ny):
+        weak = weak_record(lbm, slabs, dist, rank, world, local_rank, peak, max_over_ranks)
+    shipped = None
+    if not args.no_shipped and world == 1 and rank == 0 and not (args.nx or args.ny):
+        shipped = shipped_records(lbm)
 
     if rank != 0:
         if dist is not None:
@@ -346,11 +585,6 @@ def main():
         return
 
     # ---- roofline ------------------------------------------------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     launch_ms = ms / K  # one sweep launch per step per GPU
     achieved = (cells / world) * BYTES_PER_CELL / (launch_ms * 1e-3) / 1e9
     traffic = None
@@ -358,13 +592,15 @@ def main():
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            if tj.get("cells_per_launch") == cells // world:
-                traffic = tj.get("dram_bytes_per_launch")
+            for entry in tj.get("entries", [tj]):
+                if entry.get("cells_per_launch") == cells // world and bool(entry.get("multi", False)) == (world > 1 or args.local_slabs > 1):
+                    traffic = entry.get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
+    multi = world > 1 or args.local_slabs > 1
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "kernel": f"lbm::sweep_kernel<SWEEP_{variant.upper()},{'true' if world > 1 or args.local_slabs > 1 else 'false'}>",
+                "kernel": f"lbm::sweep_kernel<SWEEP_{variant.upper()},{'true' if multi else 'false'}>",
                 "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": cells // world,
                 "avg_launch_ms": round(launch_ms, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
                 "context": "best plain copy measured on this pool with tools/probes/stream_probe.cu: 6920 GB/s "
@@ -374,15 +610,17 @@ def main():
         "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "nx": nx, "ny": ny, "density": DENSITY, "accel": ACCEL, "omega": OMEGA,
-                   "seed": SEED, "solid_prob": SOLID_PROB, "partition": f"{world} row slab(s)",
-                   "l2": (f"working set (2 x {cells * 36 / 1e9 / world:.2f} GB lattices per GPU) >> 126 MB L2: no flush needed "
-                          "between steps" if cells * 72 / world > 4 * 126e6 else
-                          "development override: the lattices fit in L2 (latency-bound small grid, not the benchmark)"),
-                   "kernel_variant": variant, "av_vels_last": av_last,
-                   "wall_ms_per_step": round(wall * 1e3 / K, 4)},
+        "config": workload_config(name, nx, ny),
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches * world), "clocks": clocks,
+        "detail": {"partition": f"{world} row slab(s), one per GPU" if args.local_slabs <= 1 else f"{args.local_slabs} row slabs on one GPU",
+                   "kernel_variant": variant, "av_vels_last": av_last, "wall_ms_per_step": round(wall * 1e3 / K, 4)},
     }
+    if parity is not None:
+        line["parity"] = parity
+    if weak is not None:
+        line["weak"] = weak
+    if shipped is not None:
+        line["shipped"] = shipped
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(nx, ny, args.cpu_seconds, lbm)
         ref = reference_program_baseline()
@@ -391,6 +629,15 @@ def main():
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    bad = []
+    if parity is not None and not parity["ok"]:
+        bad.append("parity")
+    if shipped is not None and any(r["check_py"] != "pass" or not r["lattice_sha256_equals_oracle"] for r in shipped):
+        bad.append("shipped")
+    if weak is not None and not weak["finite"]:
+        bad.append("weak")
+    if bad:
+        raise SystemExit(f"bench.py: FAILED checks: {', '.join(bad)} (see the JSON line)")
 
 
 if __name__ == "__main__":

@@ -133,6 +133,19 @@ int lbm_download_tot_u(lbm_handle *h, double *tot_u);
  * the host only has to format text.  Rows as for lbm_download. */
 int lbm_download_fields(lbm_handle *h, float *fields);
 
+/* Prepare once, run many.  The reference compiles and serialises its solver once (main/LbmPoplibs.cpp:375-389) and
+ * lbm_runner deserialises it with --exe (main/LbmRunner.cpp:20,75-84).  Here lbm_save writes the prepared problem and
+ * its current state -- parameters, obstacles, lattice, step counter and the per-step sums so far -- to `path`, and
+ * lbm_load creates a solver from such a file on num_gpus GPUs (any number: the file holds host interchange formats,
+ * not device layouts).  A loaded solver continues exactly where the saved one stopped: lattice bit-identical, av_vels
+ * of all steps identical to an uninterrupted run on the same number of GPUs.  Not available to a rank-mode handle
+ * that owns only part of the grid.  (Within one handle, the time loop of small grids is also kept as an instantiated
+ * CUDA graph and replayed by every later lbm_run: LBM_B200_GRAPH=0 disables, =1 forces it for any size.) */
+int lbm_save(lbm_handle *h, const char *path);
+int lbm_load(lbm_handle **out, const char *path, int num_gpus);
+/* the problem a handle was created (or loaded) for; any pointer may be NULL */
+int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density, float *accel, float *omega);
+
 /* Self-test of the kernels' IEEE division / square-root helpers against CUDA's __fdiv_rn / __fsqrt_rn on
  * GPU `device`: exhaustive for x/9, x/36 and sqrt(x), `pairs` random operand pairs for a/b.
  * counts[7] = {x/9 mismatches, sqrt mismatches, a/b mismatches, x/36 mismatches, #x/9, #sqrt, #a/b}. */
@@ -141,13 +154,31 @@ int lbm_selftest_math(int device, unsigned long long pairs, unsigned long long *
 /* pinned host memory for callers that want full-speed uploads/downloads */
 void *lbm_host_alloc(size_t bytes);
 void lbm_host_free(void *p);
+/* the same, placed on the NUMA node of GPU `device`'s PCIe root when the OS allows it (free with lbm_host_free) */
+void *lbm_host_alloc_near(size_t bytes, int device);
+/* restrict the calling thread to the CPUs local to GPU `device`; returns the NUMA node (>= 0) or a negative code when
+ * the topology is unknown or the call is refused.  Optimisation only. */
+int lbm_bind_thread_near(int device);
 
 /* ------------------------------------------------------------------------------------------------
  * One process per GPU (torchrun): each rank owns one row slab; neighbours' lattices are mapped with
  * CUDA IPC and the sweep kernel stores its outgoing halo rows straight into peer memory over
- * NVLink.  Protocol:  create_rank -> ipc_export -> (all-gather the blobs) -> ipc_connect ->
- * upload/init_synthetic -> (barrier) -> run ... ; lbm_upload/lbm_download then take/return only the
- * owned rows: float[row_count][nx][9] and uint8[row_count][nx].
+ * NVLink.  lbm_upload/lbm_download then take/return only the owned rows: float[row_count][nx][9] and
+ * uint8[row_count][nx].  Protocol (B = a barrier across all ranks, the caller's job -- the library has no
+ * communicator of its own):
+ *
+ *   create_rank -> ipc_export -> (all-gather the blobs) -> ipc_connect -> B
+ *   upload | init_synthetic                 resets this rank's halo flags
+ *   B                                       every rank's lattice and flags are in place before anyone pushes a halo
+ *   run ... run, download                   no barrier needed between these
+ *   B -> upload | init_synthetic -> B       RE-UPLOAD: the barrier BEFORE it guarantees that no neighbour is still
+ *                                           pushing halo rows or epochs of the previous job into the slab being reset
+ *   B -> ipc_disconnect -> B -> destroy     TEARDOWN: all ranks finished running; every rank closes its mappings of
+ *                                           the neighbours' slabs; only then may a slab be freed (freeing memory that
+ *                                           another process still has mapped is undefined behaviour in CUDA)
+ *
+ * lbm-graphcore_b200/slabs.py (connect_ring, upload barrier helpers, close_ring) implements this over
+ * torch.distributed.
  * ---------------------------------------------------------------------------------------------- */
 
 int lbm_create_rank(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel,
@@ -156,6 +187,9 @@ size_t lbm_ipc_blob_bytes(void);
 int lbm_ipc_export(lbm_handle *h, void *blob);
 /* blobs: world * lbm_ipc_blob_bytes() bytes, rank-major */
 int lbm_ipc_connect(lbm_handle *h, const void *blobs);
+/* waits for this rank's queued work, then closes its mappings of the neighbours' slabs (first half of the
+ * teardown above).  Afterwards the handle can only be downloaded from and destroyed. */
+int lbm_ipc_disconnect(lbm_handle *h);
 
 #ifdef __cplusplus
 }

@@ -34,8 +34,8 @@ ABI_SYMBOLS = (
     "lbm_create", "lbm_upload", "lbm_run", "lbm_download", "lbm_elapsed_ms", "lbm_destroy",
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
-    "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_create_rank", "lbm_ipc_blob_bytes",
-    "lbm_ipc_export", "lbm_ipc_connect", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
+    "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_host_alloc_near", "lbm_bind_thread_near", "lbm_create_rank", "lbm_ipc_blob_bytes",
+    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_problem", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
 )
 
 
@@ -84,9 +84,16 @@ def _load() -> ctypes.CDLL:
     lib.lbm_host_alloc.restype = c_void_p
     lib.lbm_host_free.argtypes = [c_void_p]
     lib.lbm_host_free.restype = None
+    lib.lbm_host_alloc_near.argtypes = [ctypes.c_size_t, c_int]
+    lib.lbm_host_alloc_near.restype = c_void_p
+    lib.lbm_bind_thread_near.argtypes = [c_int]
     lib.lbm_ipc_blob_bytes.restype = ctypes.c_size_t
     lib.lbm_ipc_export.argtypes = [c_void_p, c_void_p]
     lib.lbm_ipc_connect.argtypes = [c_void_p, c_void_p]
+    lib.lbm_ipc_disconnect.argtypes = [c_void_p]
+    lib.lbm_save.argtypes = [c_void_p, ctypes.c_char_p]
+    lib.lbm_load.argtypes = [P(c_void_p), ctypes.c_char_p, c_int]
+    lib.lbm_problem.argtypes = [c_void_p, P(c_int), P(c_int), P(c_int), P(c_float), P(c_float), P(c_float)]
     lib.lbm_selftest_math.argtypes = [c_int, ctypes.c_ulonglong, P(ctypes.c_ulonglong)]
     return lib
 
@@ -107,6 +114,11 @@ def selftest_math(device: int = 0, pairs: int = 1 << 32) -> dict:
             "div_n": c[6]}
 
 
+def host_alloc(nbytes: int, device: int | None = None) -> int:
+    """Pinned host memory (address, or 0/None on failure); near GPU `device`'s NUMA node when given. Free with lib.lbm_host_free."""
+    return lib.lbm_host_alloc(nbytes) if device is None else lib.lbm_host_alloc_near(nbytes, device)
+
+
 def device_count() -> int:
     """Number of CUDA devices the library can see (0 when there is none)."""
     n = ctypes.c_int(0)
@@ -114,7 +126,8 @@ def device_count() -> int:
     return n.value if rc == 0 else 0
 
 
-from .problem import NSPEEDS, Params, initial_cells, load_obstacles, synthetic_obstacles  # noqa: E402,F401
+from .problem import (NSPEEDS, Params, initial_cells, load_obstacles, perturbed_problem,  # noqa: E402,F401
+                      synthetic_obstacles)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -140,6 +153,24 @@ class Solver:
         rb, rc = ctypes.c_int(), ctypes.c_int()
         _check(lib.lbm_rows(self._h, ctypes.byref(rb), ctypes.byref(rc)))
         self.row_begin, self.row_count = rb.value, rc.value
+
+    @classmethod
+    def load(cls, path: str, num_gpus: int = 1, reynolds_dim: int = 10) -> "Solver":
+        """lbm_load: a solver restored from a file written by save() (the reference's --exe)."""
+        self = cls.__new__(cls)
+        self._h = ctypes.c_void_p()
+        _check(lib.lbm_load(ctypes.byref(self._h), os.fsencode(path), num_gpus))
+        nx, ny, it = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        d, a, o = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        _check(lib.lbm_problem(self._h, ctypes.byref(nx), ctypes.byref(ny), ctypes.byref(it), ctypes.byref(d),
+                               ctypes.byref(a), ctypes.byref(o)))
+        self.params = Params(nx.value, ny.value, it.value, reynolds_dim, d.value, a.value, o.value)
+        self.row_begin, self.row_count = 0, ny.value
+        return self
+
+    def save(self, path: str) -> None:
+        """lbm_save: problem + current state, resumable with Solver.load."""
+        _check(lib.lbm_save(self._h, os.fsencode(path)))
 
     # -- lifetime -----------------------------------------------------------------------------------
     def close(self) -> None:
@@ -253,3 +284,7 @@ class Solver:
     def ipc_connect(self, blobs: bytes) -> None:
         buf = ctypes.create_string_buffer(blobs, len(blobs))
         _check(lib.lbm_ipc_connect(self._h, buf))
+
+    def ipc_disconnect(self) -> None:
+        """First half of the rank-mode teardown: close the mappings of the neighbours' slabs (then barrier, then close)."""
+        _check(lib.lbm_ipc_disconnect(self._h))

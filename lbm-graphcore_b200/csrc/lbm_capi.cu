@@ -7,6 +7,7 @@
 #include "lbm_kernels.cuh"
 
 #include <algorithm>
+#include <cctype>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +15,10 @@
 #include <new>
 #include <string>
 #include <vector>
+
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 namespace {
 
@@ -37,11 +42,13 @@ int fail(int code, const char *fmt, ...) {
   } while (0)
 
 enum { KERNEL_SCALAR = lbm::SWEEP_SCALAR, KERNEL_VEC4 = lbm::SWEEP_VEC4, KERNEL_HYBRID = lbm::SWEEP_HYBRID };
-// LBM_B200_DEBUG_SYNC=1: synchronise after every kernel launch and name the kernel that failed
+// LBM_B200_DEBUG_SYNC=1: synchronise after every kernel launch and name the kernel that failed (read once: the
+// check sits inside the per-timestep launch loop)
+const bool g_debug_sync = getenv("LBM_B200_DEBUG_SYNC") != nullptr;
 #define KERNEL_CHECK(stream, name)                                                                      \
   do {                                                                                                   \
     cudaError_t e_ = cudaGetLastError();                                                                 \
-    if (e_ == cudaSuccess && getenv("LBM_B200_DEBUG_SYNC")) e_ = cudaStreamSynchronize(stream);          \
+    if (e_ == cudaSuccess && g_debug_sync) e_ = cudaStreamSynchronize(stream);                           \
     if (e_ != cudaSuccess) return fail(LBM_E_CUDA, "kernel %s failed: %s", name, cudaGetErrorString(e_)); \
   } while (0)
 
@@ -60,6 +67,7 @@ struct Slab {
   // upload/download pipeline: the staging buffer is used as two halves; PCIe copies run on copy_stream while the
   // transposition kernel of the other half runs on `stream`
   cudaStream_t copy_stream = nullptr;
+  int stage_chunk = 0;  // chunks enqueued since the last drain (which half of the staging buffer is next)
   cudaEvent_t filled[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
   // one exported allocation: [lattice 0][lattice 1][flags]
   char *base = nullptr;
@@ -75,6 +83,7 @@ struct Slab {
   unsigned *ticket = nullptr;      // [1..2] edge tickets (multi-slab)
   int *step = nullptr;         // [1] error flag set by a kernel that gave up waiting ([0] unused)
   unsigned long long *barrier = nullptr;  // persistent kernel: grid-barrier arrivals since the last upload
+  unsigned long long barrier_arrivals = 0;  // host copy of what *barrier holds when the queued launches have finished
   int persistent_grid = 0;     // > 0: the whole time loop runs as one cooperative launch of this many CTAs
   unsigned long long *free_dev = nullptr;
   float *stage = nullptr;
@@ -85,12 +94,22 @@ struct Slab {
   int *flag_to_north = nullptr;
   int south_ghost_row = 0;
   // launch configuration
-  int kernel = 0;  // KERNEL_SCALAR / KERNEL_VEC4
+  int kernel = 0;  // KERNEL_SCALAR / KERNEL_VEC4 / KERNEL_HYBRID
   int tiles_y = 1; // tile rows this slab sweeps = ceil((nyl + 2) / 8)
   int grid = 1;    // one CTA per tile
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long free_cells = 0;
 };
+
+// replay unit of the time loop on one stream: kGraphSteps timesteps of every slab that runs on it
+struct StreamGraph {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};
+  long long nodes = 0;  // kernel launches one replay stands for
+};
+constexpr int kGraphSteps = 2 * lbm::kWindowSteps;  // even: a replay leaves the lattice parity unchanged
+constexpr long long kGraphMaxCells = 8ll << 20;     // per slab: above this a step takes >> a launch, nothing to gain
 
 }  // namespace
 
@@ -111,9 +130,14 @@ struct lbm_handle {
   int cur = 0;  // which lattice holds the current state
   int steps_done = 0;
   bool uploaded = false;
-  bool first_run_pending = false;
+  bool first_run_pending = false;  // the one-off guarded accelerate_flow has not been applied yet
+  bool halo_pending = false;       // the ghost rows of the current lattice (and the first epoch) have not been published yet
   double last_ms = 0.0;
   long long launches = 0;
+  // time loop as a CUDA graph (one per distinct stream and per lattice parity), built on first use and replayed
+  bool graph_capture = false;      // launches are being captured: kernels take the step number from device memory
+  int graph_state[2] = {0, 0};     // per parity: 0 not built, 1 ready, -1 unavailable
+  std::vector<StreamGraph> graphs;
 };
 
 namespace {
@@ -139,7 +163,8 @@ int configure_launch(lbm_handle *h, Slab &s) {
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
     CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device));
     if (coop && sms > 0) {
-      // one CTA per SM at most (the barrier costs one atomic per CTA); tile rows are dealt over all their warps
+      // LBM_PERSIST_MINB (2) CTAs per SM at most -- the barrier costs one atomic per CTA; tile rows are dealt over
+      // all their warps
       const int units = s.grid * lbm::kTileH;
       int ctas = std::min(std::min(LBM_PERSIST_MINB * sms, kPersistentMaxCtas), units);
       if (const char *e = getenv("LBM_B200_PERSIST_CTAS")) ctas = std::max(1, std::min(atoi(e), ctas));
@@ -252,6 +277,7 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   a.w1 = h->density * h->accel / 9.f;               // main/LastChance.cpp:158
   a.w2 = h->density * h->accel / 36.f;              // :159
   a.t = h->steps_done;  // launch_sweep overrides it for every step of a run
+  a.t_base = h->graph_capture ? s.step : nullptr;
   a.partials = s.partials;
   a.tot_u = s.tot_u;
   a.edge_ticket = s.ticket + 1;
@@ -285,7 +311,8 @@ int flush_reductions(lbm_handle *h, Slab &s) {
   if (s.window_count == 0) return LBM_OK;
   lbm::reduce_rows_kernel<<<dim3((unsigned)s.tiles_y, (unsigned)s.window_count), 256, 0, s.stream>>>(s.partials, s.row_partials, h->ntx,
                                                                                                  s.tiles_y);
-  lbm::reduce_total_kernel<<<(unsigned)s.window_count, 256, 0, s.stream>>>(s.row_partials, s.tot_u + s.window_first, s.tiles_y);
+  lbm::reduce_total_kernel<<<(unsigned)s.window_count, 256, 0, s.stream>>>(s.row_partials, s.tot_u, s.tiles_y, s.window_first,
+                                                                           h->graph_capture ? s.step : nullptr);
   h->launches += 2;
   KERNEL_CHECK(s.stream, "reduce_rows/reduce_total");
   s.window_first += s.window_count;
@@ -327,8 +354,8 @@ int launch_persistent(lbm_handle *h, Slab &s, int iters) {
   lbm::SweepArgs a = sweep_args(h, s);
   float *buf_in = s.buf[h->cur], *buf_out = s.buf[h->cur ^ 1];
   int t0 = h->steps_done, steps = iters;
-  unsigned long long *bar = s.barrier;
-  void *args[] = {&a, &buf_in, &buf_out, &t0, &steps, &bar};
+  unsigned long long *bar = s.barrier, bar0 = s.barrier_arrivals;
+  void *args[] = {&a, &buf_in, &buf_out, &t0, &steps, &bar, &bar0};
   const void *fn = s.kernel == KERNEL_VEC4     ? (const void *)lbm::sweep_persistent_kernel<lbm::SWEEP_VEC4>
                    : s.kernel == KERNEL_HYBRID ? (const void *)lbm::sweep_persistent_kernel<lbm::SWEEP_HYBRID>
                                                : (const void *)lbm::sweep_persistent_kernel<lbm::SWEEP_SCALAR>;
@@ -340,6 +367,7 @@ int launch_persistent(lbm_handle *h, Slab &s, int iters) {
     return LBM_OK;
   }
   if (e != cudaSuccess) return fail(LBM_E_CUDA, "cooperative launch of the persistent sweep failed: %s", cudaGetErrorString(e));
+  s.barrier_arrivals += (unsigned long long)iters * (unsigned long long)s.persistent_grid;
   ++h->launches;
   KERNEL_CHECK(s.stream, "sweep_persistent");
   return LBM_OK;
@@ -435,6 +463,7 @@ int reset_counters(lbm_handle *h) {
     s.window_count = 0;
     CUDA_TRY(cudaMemsetAsync(s.step, 0, 2 * sizeof(int), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.barrier, 0, sizeof(unsigned long long), s.stream));
+    s.barrier_arrivals = 0;
     CUDA_TRY(cudaMemsetAsync(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.free_dev, 0, sizeof(unsigned long long), s.stream));
   }
@@ -453,6 +482,7 @@ int finish_upload(lbm_handle *h) {
   }
   h->uploaded = true;
   h->first_run_pending = true;
+  h->halo_pending = true;
   return LBM_OK;
 }
 
@@ -631,6 +661,29 @@ int lbm_ipc_connect(lbm_handle *h, const void *blobs) {
   return LBM_OK;
 }
 
+// Teardown of the one-process-per-GPU mode is two-phase (see the protocol in include/lbm_b200.h): every rank first
+// drops its mappings of the neighbours' slabs, the ranks meet at a barrier, and only then does anyone free the
+// allocation its neighbours had mapped (freeing memory that another process still has open through
+// cudaIpcOpenMemHandle is undefined behaviour).
+int lbm_ipc_disconnect(lbm_handle *h) {
+  if (!h) return fail(LBM_E_ARG, "null argument");
+  if (!h->rank_mode) return fail(LBM_E_STATE, "lbm_ipc_disconnect needs a handle from lbm_create_rank");
+  for (Slab &s : h->slabs) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    if (s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (s.copy_stream) CUDA_TRY(cudaStreamSynchronize(s.copy_stream));
+  }
+  for (void *p : h->ipc_opened) CUDA_TRY(cudaIpcCloseMemHandle(p));
+  h->ipc_opened.clear();
+  if (h->world > 1) {
+    Slab &s = h->slabs[0];
+    for (int b = 0; b < 2; ++b) s.south_buf[b] = s.north_buf[b] = nullptr;
+    s.flag_to_south = s.flag_to_north = nullptr;
+    h->connected = false;  // compute calls now fail with LBM_E_STATE instead of touching unmapped peer memory
+  }
+  return LBM_OK;
+}
+
 void lbm_destroy(lbm_handle *h) {
   if (!h) return;
   for (Slab &s : h->slabs) {
@@ -638,54 +691,113 @@ void lbm_destroy(lbm_handle *h) {
     if (s.stream) cudaStreamSynchronize(s.stream);
   }
   if (!h->slabs.empty()) cudaSetDevice(h->slabs[0].device);
-  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  for (StreamGraph &g : h->graphs)
+    for (cudaGraphExec_t e : g.exec)
+      if (e) { cudaSetDevice(g.device); cudaGraphExecDestroy(e); }
+  if (!h->slabs.empty()) cudaSetDevice(h->slabs[0].device);
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);  // (none left after lbm_ipc_disconnect)
   for (Slab &s : h->slabs) free_slab(s);
   cudaGetLastError();
   delete h;
 }
 
 // ---- run(0) --------------------------------------------------------------------------------------
-int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles) {
-  if (!h || !cells_aos || !obstacles) return fail(LBM_E_ARG, "null argument");
-  if (!h->connected) return fail(LBM_E_STATE, "ranks are not connected yet (lbm_ipc_connect)");
-  int rc = reset_counters(h);
-  if (rc) return rc;
+}  // extern "C"
+namespace {
+
+// Global rows [g0, g0 + n) of the problem -> the slabs that own them.  `cells` / `obstacles` point at row g0.
+int upload_rows(lbm_handle *h, int g0, int n, const float *cells, const uint8_t *obstacles) {
   const int nx = h->nx;
   for (Slab &s : h->slabs) {
+    const int lo = std::max(g0, s.row0), hi = std::min(g0 + n, s.row0 + s.nyl);
+    if (lo >= hi) continue;
     CUDA_TRY(cudaSetDevice(s.device));
-    // in rank mode the caller passes only the owned rows
-    const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
-    const float *cells = cells_aos + first * nx * lbm::kSpeeds;
-    const uint8_t *obst = obstacles + first * nx;
+    const float *c = cells + (size_t)(lo - g0) * nx * lbm::kSpeeds;
+    const uint8_t *o = obstacles + (size_t)(lo - g0) * nx;
+    const int first_storage_row = 1 + (lo - s.row0);
     // cells: AoS rows -> tiles; obstacles: bytes -> bits.  Chunks of whole rows, PCIe copy of one half of the
     // staging buffer overlapped with the transposition of the other
-    int chunk = 0;
-    rc = stage_in(s, reinterpret_cast<const char *>(cells), (size_t)nx * lbm::kSpeeds * sizeof(float), s.nyl, chunk,
-                  [&](char *stage, int r, int rows) {
-                    lbm::aos_to_tiles_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(reinterpret_cast<const float *>(stage), s.buf[0],
-                                                                                        h->ntx, nx, rows, 1 + r);
-                    ++h->launches;
-                    KERNEL_CHECK(s.stream, "aos_to_tiles");
-                    return (int)LBM_OK;
-                  });
+    int rc = stage_in(s, reinterpret_cast<const char *>(c), (size_t)nx * lbm::kSpeeds * sizeof(float), hi - lo, s.stage_chunk,
+                      [&](char *stage, int r, int rows) {
+                        lbm::aos_to_tiles_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
+                            reinterpret_cast<const float *>(stage), s.buf[0], h->ntx, nx, rows, first_storage_row + r);
+                        ++h->launches;
+                        KERNEL_CHECK(s.stream, "aos_to_tiles");
+                        return (int)LBM_OK;
+                      });
     if (rc) return rc;
     const int words = (nx + 31) / 32;
-    rc = stage_in(s, reinterpret_cast<const char *>(obst), (size_t)nx, s.nyl, chunk, [&](char *stage, int r, int rows) {
+    rc = stage_in(s, reinterpret_cast<const char *>(o), (size_t)nx, hi - lo, s.stage_chunk, [&](char *stage, int r, int rows) {
       const long long threads = (long long)rows * words * 32;
-      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(reinterpret_cast<const uint8_t *>(stage), s.mask,
-                                                                                  h->ntx, nx, rows, 1 + r, s.free_dev);
+      lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
+          reinterpret_cast<const uint8_t *>(stage), s.mask, h->ntx, nx, rows, first_storage_row + r, s.free_dev);
       ++h->launches;
       KERNEL_CHECK(s.stream, "pack_mask");
       return (int)LBM_OK;
     });
     if (rc) return rc;
   }
-  // all slabs' pipelines were only enqueued above (they overlap across GPUs); wait for them here
+  return LBM_OK;
+}
+// all slabs' pipelines were only enqueued (they overlap across GPUs); wait for them
+int drain_all(lbm_handle *h) {
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
-    rc = drain_stages(s);
+    int rc = drain_stages(s);
     if (rc) return rc;
+    s.stage_chunk = 0;
   }
+  return LBM_OK;
+}
+// Global rows [g0, g0 + n) of the current state -> host AoS / obstacle bytes (either may be null)
+int download_rows(lbm_handle *h, int g0, int n, float *cells, uint8_t *obstacles) {
+  const int nx = h->nx;
+  for (Slab &s : h->slabs) {
+    const int lo = std::max(g0, s.row0), hi = std::min(g0 + n, s.row0 + s.nyl);
+    if (lo >= hi) continue;
+    CUDA_TRY(cudaSetDevice(s.device));
+    const int first_storage_row = 1 + (lo - s.row0);
+    if (cells) {
+      int rc = stage_out(s, reinterpret_cast<char *>(cells + (size_t)(lo - g0) * nx * lbm::kSpeeds),
+                         (size_t)nx * lbm::kSpeeds * sizeof(float), hi - lo, s.stage_chunk, [&](char *stage, int r, int rows) {
+                           lbm::tiles_to_aos_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
+                               s.buf[h->cur], reinterpret_cast<float *>(stage), h->ntx, nx, rows, first_storage_row + r);
+                           ++h->launches;
+                           KERNEL_CHECK(s.stream, "tiles_to_aos");
+                           return (int)LBM_OK;
+                         });
+      if (rc) return rc;
+    }
+    if (obstacles) {
+      int rc = stage_out(s, reinterpret_cast<char *>(obstacles + (size_t)(lo - g0) * nx), (size_t)nx, hi - lo, s.stage_chunk,
+                         [&](char *stage, int r, int rows) {
+                           const long long cellsn = (long long)rows * nx;
+                           lbm::unpack_mask_kernel<<<(unsigned)((cellsn + 255) / 256), 256, 0, s.stream>>>(
+                               s.mask, reinterpret_cast<uint8_t *>(stage), h->ntx, nx, rows, first_storage_row + r);
+                           ++h->launches;
+                           KERNEL_CHECK(s.stream, "unpack_mask");
+                           return (int)LBM_OK;
+                         });
+      if (rc) return rc;
+    }
+  }
+  return LBM_OK;
+}
+
+}  // namespace
+extern "C" {
+
+int lbm_upload(lbm_handle *h, const float *cells_aos, const uint8_t *obstacles) {
+  if (!h || !cells_aos || !obstacles) return fail(LBM_E_ARG, "null argument");
+  if (!h->connected) return fail(LBM_E_STATE, "ranks are not connected yet (lbm_ipc_connect)");
+  int rc = reset_counters(h);
+  if (rc) return rc;
+  // in rank mode the caller passes only the owned rows
+  if (h->rank_mode) rc = upload_rows(h, h->slabs[0].row0, h->slabs[0].nyl, cells_aos, obstacles);
+  else rc = upload_rows(h, 0, h->ny, cells_aos, obstacles);
+  if (rc) return rc;
+  rc = drain_all(h);
+  if (rc) return rc;
   return finish_upload(h);
 }
 
@@ -712,12 +824,136 @@ int lbm_init_synthetic(lbm_handle *h, uint64_t seed, float solid_prob) {
 }
 
 // ---- run(1) --------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+
+// slabs that share a stream (several slabs on one device) alternate in it, so a sweep is not preceded by a
+// sweep of the same slab: no dependent-launch overlap there (the flag waits need the other slab to finish)
+bool shares_a_stream(const lbm_handle *h) {
+  for (size_t i = 0; i < h->slabs.size(); ++i)
+    for (size_t j = 0; j < i; ++j)
+      if (h->slabs[i].stream == h->slabs[j].stream) return true;
+  return false;
+}
+
+// `n` timesteps starting at step number t0 (relative to *t_base while capturing), one launch per slab per timestep,
+// slabs interleaved so no GPU's queue runs ahead of its neighbours
+int enqueue_steps(lbm_handle *h, int t0, int n, bool shared_stream) {
+  for (int t = 0; t < n; ++t) {
+    for (Slab &s : h->slabs) {
+      if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
+      int rc = launch_sweep(h, s, t0 + t, t > 0 && !shared_stream);
+      if (rc) return rc;
+    }
+    h->cur ^= 1;
+  }
+  for (Slab &s : h->slabs) {
+    if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
+    int rc = flush_reductions(h, s);
+    if (rc) return rc;
+  }
+  return LBM_OK;
+}
+
+// Capture kGraphSteps timesteps of the loop above once per distinct stream and keep the instantiated graphs in the
+// handle ("prepare once, run many": a re-run or a long run replays them instead of re-enqueueing every launch; cf. the
+// reference's whole time loop being one pre-compiled device program, main/LbmAoS.cpp:353-356).  The captured kernels
+// read the step number from s.step[0] (set before the first replay, advanced by the last node of every replay), so
+// one graph serves any position in the run; it bakes in the lattice parity, hence one graph per parity.
+// On any failure graphs are switched off for this parity and the caller falls back to plain launches.
+int build_graphs(lbm_handle *h, int parity) {
+  if (h->graphs.empty()) {
+    for (Slab &s : h->slabs) {
+      bool seen = false;
+      for (StreamGraph &g : h->graphs) seen |= (g.stream == s.stream);
+      if (seen) continue;
+      StreamGraph g;
+      g.device = s.device;
+      g.stream = s.stream;
+      h->graphs.push_back(g);
+    }
+  }
+  const int cur0 = h->cur;
+  const long long launches0 = h->launches;
+  std::vector<int> first0;
+  for (Slab &s : h->slabs) first0.push_back(s.window_first);
+  bool ok = true;
+  size_t begun = 0;
+  for (StreamGraph &g : h->graphs) {
+    if (cudaSetDevice(g.device) != cudaSuccess || cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      ok = false;
+      break;
+    }
+    ++begun;
+  }
+  h->graph_capture = true;
+  if (ok) ok = enqueue_steps(h, 0, kGraphSteps, shares_a_stream(h)) == LBM_OK;
+  if (ok) {
+    for (Slab &s : h->slabs) {
+      if (cudaSetDevice(s.device) != cudaSuccess) { ok = false; break; }
+      lbm::advance_step_kernel<<<1, 1, 0, s.stream>>>(s.step, kGraphSteps);
+      ++h->launches;
+      ok = ok && cudaGetLastError() == cudaSuccess;
+    }
+  }
+  h->graph_capture = false;
+  for (size_t i = 0; i < begun; ++i) {
+    StreamGraph &g = h->graphs[i];
+    cudaGraph_t graph = nullptr;
+    cudaSetDevice(g.device);
+    if (cudaStreamEndCapture(g.stream, &graph) != cudaSuccess || !graph) ok = false;
+    if (ok && cudaGraphInstantiate(&g.exec[parity], graph, 0) != cudaSuccess) {
+      g.exec[parity] = nullptr;
+      ok = false;
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+  cudaGetLastError();
+  // nothing ran: put the bookkeeping back
+  const long long per_replay = h->launches - launches0;
+  h->launches = launches0;
+  h->cur = cur0;
+  for (size_t i = 0; i < h->slabs.size(); ++i) {
+    h->slabs[i].window_first = first0[i];
+    h->slabs[i].window_count = 0;
+  }
+  if (!ok) {
+    for (StreamGraph &g : h->graphs)
+      if (g.exec[parity]) { cudaGraphExecDestroy(g.exec[parity]); g.exec[parity] = nullptr; }
+    h->graph_state[parity] = -1;
+    return LBM_OK;
+  }
+  for (StreamGraph &g : h->graphs) g.nodes = per_replay / (long long)h->graphs.size();
+  h->graph_state[parity] = 1;
+  return LBM_OK;
+}
+
+bool graphs_wanted(const lbm_handle *h, int iters) {
+  static const int env = getenv("LBM_B200_GRAPH") ? atoi(getenv("LBM_B200_GRAPH")) : -1;  // 0 off, 1 force, default auto
+  if (env == 0 || g_debug_sync || iters < kGraphSteps) return false;
+  if (env == 1) return true;
+  for (const Slab &s : h->slabs)
+    if ((long long)s.nyl * h->nx > kGraphMaxCells) return false;
+  return true;
+}
+
+}  // namespace
+extern "C" {
+
 int lbm_run(lbm_handle *h, int iters) {
   if (!h) return fail(LBM_E_ARG, "null argument");
   if (!h->uploaded) return fail(LBM_E_STATE, "lbm_run before lbm_upload");
+  if (!h->connected) return fail(LBM_E_STATE, "ranks are not connected (lbm_ipc_connect; or already disconnected)");
   if (iters < 0 || h->steps_done + iters > h->max_iters)
     return fail(LBM_E_ARG, "cannot run %d more steps: %d of max_iters=%d already done", iters, h->steps_done,
                 h->max_iters);
+  const bool persistent = h->slabs.size() == 1 && h->slabs[0].persistent_grid > 0 && iters > 0;
+  // build (once) the replayable time loop before the timed region starts
+  const bool use_graphs = !persistent && graphs_wanted(h, iters);
+  if (use_graphs && h->graph_state[h->cur] == 0) {
+    int rc = build_graphs(h, h->cur);
+    if (rc) return rc;
+  }
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
@@ -735,22 +971,26 @@ int lbm_run(lbm_handle *h, int iters) {
       ++h->launches;
       KERNEL_CHECK(s.stream, "accelerate_flow");
     }
-    // ... then the initial halo: every slab fills its neighbours' ghost rows and publishes epoch 1
+    h->first_run_pending = false;
+  }
+  if (h->halo_pending) {
+    // ... then the initial halo of a fresh (or re-loaded) lattice: every slab fills its neighbours' ghost rows and
+    // publishes the epoch the next timestep waits for
     for (Slab &s : h->slabs) {
       CUDA_TRY(cudaSetDevice(s.device));
       lbm::init_halo_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(s.buf[h->cur], s.north_buf[h->cur], s.south_buf[h->cur],
                                                                        h->ntx, h->nx, s.nyl, s.south_ghost_row);
       ++h->launches;
       if (h->multi) {
-        lbm::publish_epoch_kernel<<<1, 1, 0, s.stream>>>(s.flag_to_south, s.flag_to_north, 1);
+        lbm::publish_epoch_kernel<<<1, 1, 0, s.stream>>>(s.flag_to_south, s.flag_to_north, h->steps_done + 1);
         ++h->launches;
       }
       KERNEL_CHECK(s.stream, "init_halo/publish_epoch");
     }
-    h->first_run_pending = false;
+    h->halo_pending = false;
   }
-  // one launch per slab per timestep, slabs interleaved so no GPU's queue runs ahead of its neighbours
-  if (h->slabs.size() == 1 && h->slabs[0].persistent_grid > 0 && iters > 0) {
+  if (persistent) {
+    // a single small slab: the whole time loop is one cooperative launch
     Slab &s = h->slabs[0];
     int rc = launch_persistent(h, s, iters);
     if (rc) return rc;
@@ -759,24 +999,26 @@ int lbm_run(lbm_handle *h, int iters) {
       iters_left_for_loop = 0;
     }
   }
-  // slabs that share a stream (several slabs on one device) alternate in it, so a sweep is not preceded by a
-  // sweep of the same slab: no dependent-launch overlap there (the flag waits need the other slab to finish)
-  bool shared_stream = false;
-  for (size_t i = 0; i < h->slabs.size(); ++i)
-    for (size_t j = 0; j < i; ++j) shared_stream |= (h->slabs[i].stream == h->slabs[j].stream);
-  for (int t = 0; t < iters_left_for_loop; ++t) {
+  int t = 0;
+  if (use_graphs && h->graph_state[h->cur] == 1 && iters_left_for_loop >= kGraphSteps) {
+    const int parity = h->cur;
     for (Slab &s : h->slabs) {
-      if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
-      int rc = launch_sweep(h, s, h->steps_done + t, t > 0 && !shared_stream);
-      if (rc) return rc;
+      CUDA_TRY(cudaSetDevice(s.device));
+      lbm::set_step_kernel<<<1, 1, 0, s.stream>>>(s.step, h->steps_done);
+      ++h->launches;
+      KERNEL_CHECK(s.stream, "set_step");
     }
-    h->cur ^= 1;
+    for (; iters_left_for_loop - t >= kGraphSteps; t += kGraphSteps) {
+      for (StreamGraph &g : h->graphs) {
+        if (h->graphs.size() > 1) CUDA_TRY(cudaSetDevice(g.device));
+        CUDA_TRY(cudaGraphLaunch(g.exec[parity], g.stream));
+        h->launches += g.nodes;
+      }
+    }
+    for (Slab &s : h->slabs) s.window_first = h->steps_done + t;
   }
-  for (Slab &s : h->slabs) {
-    if (h->slabs.size() > 1) CUDA_TRY(cudaSetDevice(s.device));
-    int rc = flush_reductions(h, s);
-    if (rc) return rc;
-  }
+  int rc = enqueue_steps(h, h->steps_done + t, iters_left_for_loop - t, shares_a_stream(h));
+  if (rc) return rc;
   h->steps_done += iters;
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
@@ -829,27 +1071,12 @@ int lbm_download(lbm_handle *h, float *cells_aos, float *av_vels) {
   if (av_vels && h->rank_mode && h->world > 1)
     return fail(LBM_E_ARG, "with one process per GPU av_vels needs all ranks: use lbm_download_tot_u and "
                            "combine in rank order");
-  const int nx = h->nx;
   if (cells_aos) {
-    for (Slab &s : h->slabs) {
-      CUDA_TRY(cudaSetDevice(s.device));
-      const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
-      int chunk = 0;
-      int rc = stage_out(s, reinterpret_cast<char *>(cells_aos + first * nx * lbm::kSpeeds), (size_t)nx * lbm::kSpeeds * sizeof(float),
-                         s.nyl, chunk, [&](char *stage, int r, int rows) {
-                           lbm::tiles_to_aos_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
-                               s.buf[h->cur], reinterpret_cast<float *>(stage), h->ntx, nx, rows, 1 + r);
-                           ++h->launches;
-                           KERNEL_CHECK(s.stream, "tiles_to_aos");
-                           return (int)LBM_OK;
-                         });
-      if (rc) return rc;
-    }
-    for (Slab &s : h->slabs) {
-      CUDA_TRY(cudaSetDevice(s.device));
-      int rc = drain_stages(s);
-      if (rc) return rc;
-    }
+    int rc = h->rank_mode ? download_rows(h, h->slabs[0].row0, h->slabs[0].nyl, cells_aos, nullptr)
+                          : download_rows(h, 0, h->ny, cells_aos, nullptr);
+    if (rc) return rc;
+    rc = drain_all(h);
+    if (rc) return rc;
   }
   if (av_vels) {
     std::vector<double> tot(std::max(h->steps_done, 1));
@@ -870,8 +1097,7 @@ int lbm_download_fields(lbm_handle *h, float *fields) {
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
-    int chunk = 0;
-    int rc = stage_out(s, reinterpret_cast<char *>(fields + first * nx * 4), (size_t)nx * 4 * sizeof(float), s.nyl, chunk,
+    int rc = stage_out(s, reinterpret_cast<char *>(fields + first * nx * 4), (size_t)nx * 4 * sizeof(float), s.nyl, s.stage_chunk,
                        [&](char *stage, int r, int rows) {
                          lbm::final_state_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
                              s.buf[h->cur], s.mask, reinterpret_cast<float4 *>(stage), h->ntx, nx, rows, 1 + r, h->density);
@@ -881,11 +1107,135 @@ int lbm_download_fields(lbm_handle *h, float *fields) {
                        });
     if (rc) return rc;
   }
-  for (Slab &s : h->slabs) {
-    CUDA_TRY(cudaSetDevice(s.device));
-    int rc = drain_stages(s);
-    if (rc) return rc;
+  return drain_all(h);
+}
+
+// ---- prepare once / run many ------------------------------------------------------------------------
+// The reference compiles its graph once, serialises it (main/LbmPoplibs.cpp:375-389) and lbm_runner deserialises it
+// with --exe (main/LbmRunner.cpp:20,75-84).  A B200 solver has nothing to compile at run time; what is worth keeping
+// is the prepared PROBLEM and its STATE.  The file is layout-independent (host interchange formats), so it can be
+// loaded onto a different number of GPUs than it was saved from:
+//   SaveHeader | obstacles uint8[ny][nx] | cells float[ny][nx][9] (current state) | tot_u double[steps_done]
+namespace {
+struct SaveHeader {
+  char magic[8];
+  uint32_t version, header_bytes;
+  int32_t nx, ny, max_iters, steps_done;
+  float density, accel, omega;
+  int32_t first_run_pending;
+  int64_t free_cells;
+};
+constexpr char kSaveMagic[8] = {'L', 'B', 'M', 'B', '2', '0', '0', 0};
+constexpr size_t kSaveChunkBytes = 256u << 20;
+struct FileCloser {
+  FILE *f;
+  ~FileCloser() { if (f) fclose(f); }
+};
+}  // namespace
+
+int lbm_save(lbm_handle *h, const char *path) {
+  if (!h || !path) return fail(LBM_E_ARG, "null argument");
+  if (!h->uploaded) return fail(LBM_E_STATE, "lbm_save before lbm_upload");
+  if (h->rank_mode && h->world > 1)
+    return fail(LBM_E_STATE, "lbm_save needs a handle that owns the whole grid (lbm_create / lbm_create_on_devices)");
+  FileCloser fc{fopen(path, "wb")};
+  if (!fc.f) return fail(LBM_E_ARG, "cannot open %s for writing", path);
+  SaveHeader hd{};
+  memcpy(hd.magic, kSaveMagic, 8);
+  hd.version = 1;
+  hd.header_bytes = sizeof hd;
+  hd.nx = h->nx; hd.ny = h->ny; hd.max_iters = h->max_iters; hd.steps_done = h->steps_done;
+  hd.density = h->density; hd.accel = h->accel; hd.omega = h->omega;
+  hd.first_run_pending = h->first_run_pending ? 1 : 0;
+  hd.free_cells = 0;
+  for (Slab &s : h->slabs) hd.free_cells += s.free_cells;
+  if (fwrite(&hd, sizeof hd, 1, fc.f) != 1) return fail(LBM_E_ARG, "short write to %s", path);
+  const size_t row_bytes = (size_t)h->nx * lbm::kSpeeds * sizeof(float);
+  const int rows_per_chunk = (int)std::max<size_t>(1, kSaveChunkBytes / row_bytes);
+  std::vector<char> buf((size_t)std::min(rows_per_chunk, h->ny) * row_bytes);
+  for (int pass = 0; pass < 2; ++pass) {  // obstacles, then cells
+    const size_t rb = pass == 0 ? (size_t)h->nx : row_bytes;
+    for (int r = 0; r < h->ny; r += rows_per_chunk) {
+      const int n = std::min(rows_per_chunk, h->ny - r);
+      int rc = pass == 0 ? download_rows(h, r, n, nullptr, reinterpret_cast<uint8_t *>(buf.data()))
+                         : download_rows(h, r, n, reinterpret_cast<float *>(buf.data()), nullptr);
+      if (rc == LBM_OK) rc = drain_all(h);
+      if (rc) return rc;
+      if (fwrite(buf.data(), rb, (size_t)n, fc.f) != (size_t)n) return fail(LBM_E_ARG, "short write to %s", path);
+    }
   }
+  std::vector<double> tot(std::max(h->steps_done, 1));
+  int rc = lbm_download_tot_u(h, tot.data());
+  if (rc) return rc;
+  if (h->steps_done && fwrite(tot.data(), sizeof(double), (size_t)h->steps_done, fc.f) != (size_t)h->steps_done)
+    return fail(LBM_E_ARG, "short write to %s", path);
+  FILE *f = fc.f;
+  fc.f = nullptr;
+  if (fclose(f) != 0) return fail(LBM_E_ARG, "closing %s failed", path);
+  return LBM_OK;
+}
+
+int lbm_load(lbm_handle **out, const char *path, int num_gpus) {
+  if (!out || !path) return fail(LBM_E_ARG, "null argument");
+  *out = nullptr;
+  FileCloser fc{fopen(path, "rb")};
+  if (!fc.f) return fail(LBM_E_ARG, "cannot open %s", path);
+  SaveHeader hd{};
+  if (fread(&hd, sizeof hd, 1, fc.f) != 1 || memcmp(hd.magic, kSaveMagic, 8) != 0)
+    return fail(LBM_E_ARG, "%s is not a prepared-solver file", path);
+  if (hd.version != 1 || hd.header_bytes != sizeof hd)
+    return fail(LBM_E_ARG, "%s has version %u (this library reads version 1)", path, hd.version);
+  if (hd.steps_done < 0 || hd.steps_done > hd.max_iters) return fail(LBM_E_ARG, "%s: corrupt step counter", path);
+  lbm_handle *h = nullptr;
+  int rc = lbm_create(&h, hd.nx, hd.ny, hd.max_iters, hd.density, hd.accel, hd.omega, num_gpus);
+  if (rc) return rc;
+  auto bail = [&](int code) { lbm_destroy(h); return code; };
+  rc = reset_counters(h);
+  if (rc) return bail(rc);
+  const size_t row_bytes = (size_t)h->nx * lbm::kSpeeds * sizeof(float);
+  const int rows_per_chunk = (int)std::max<size_t>(1, kSaveChunkBytes / row_bytes);
+  // the obstacle bytes come first in the file but upload_rows wants both: read the obstacles whole (1 B per cell),
+  // the cells chunk by chunk
+  std::vector<uint8_t> obst((size_t)hd.nx * hd.ny);
+  if (fread(obst.data(), 1, obst.size(), fc.f) != obst.size()) return bail(fail(LBM_E_ARG, "%s is truncated (obstacles)", path));
+  std::vector<char> buf((size_t)std::min(rows_per_chunk, h->ny) * row_bytes);
+  for (int r = 0; r < h->ny; r += rows_per_chunk) {
+    const int n = std::min(rows_per_chunk, h->ny - r);
+    if (fread(buf.data(), row_bytes, (size_t)n, fc.f) != (size_t)n) return bail(fail(LBM_E_ARG, "%s is truncated (cells)", path));
+    rc = upload_rows(h, r, n, reinterpret_cast<const float *>(buf.data()), obst.data() + (size_t)r * hd.nx);
+    if (rc == LBM_OK) rc = drain_all(h);  // buf is reused by the next chunk
+    if (rc) return bail(rc);
+  }
+  rc = finish_upload(h);
+  if (rc) return bail(rc);
+  long long free_cells = 0;
+  for (Slab &s : h->slabs) free_cells += s.free_cells;
+  if (free_cells != hd.free_cells) return bail(fail(LBM_E_ARG, "%s: free-cell count does not match its obstacles", path));
+  // resume point: the saved lattice is the current state; per-step sums so far go to slab 0 (x + 0.0 is exact, so the
+  // av_vels of the steps already done come back bit for bit whatever the new partition)
+  h->steps_done = hd.steps_done;
+  h->first_run_pending = hd.first_run_pending != 0;
+  if (hd.steps_done) {
+    std::vector<double> tot((size_t)hd.steps_done);
+    if (fread(tot.data(), sizeof(double), tot.size(), fc.f) != tot.size()) return bail(fail(LBM_E_ARG, "%s is truncated (tot_u)", path));
+    Slab &s0 = h->slabs[0];
+    cudaError_t e = cudaSetDevice(s0.device);
+    if (e == cudaSuccess) e = cudaMemcpy(s0.tot_u, tot.data(), tot.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(fail(LBM_E_CUDA, "restoring tot_u: %s", cudaGetErrorString(e)));
+  }
+  for (Slab &s : h->slabs) s.window_first = hd.steps_done;
+  *out = h;
+  return LBM_OK;
+}
+
+int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density, float *accel, float *omega) {
+  if (!h) return fail(LBM_E_ARG, "null argument");
+  if (nx) *nx = h->nx;
+  if (ny) *ny = h->ny;
+  if (max_iters) *max_iters = h->max_iters;
+  if (density) *density = h->density;
+  if (accel) *accel = h->accel;
+  if (omega) *omega = h->omega;
   return LBM_OK;
 }
 
@@ -959,6 +1309,75 @@ int lbm_selftest_math(int device, unsigned long long pairs, unsigned long long *
   cudaFree(d);
   if (e != cudaSuccess) return fail(LBM_E_CUDA, "math self-test failed: %s", cudaGetErrorString(e));
   return LBM_OK;
+}
+
+}  // extern "C"
+namespace {
+// NUMA node and CPU list of the host bridge a GPU hangs off, from sysfs (-1 / "" when unknown)
+int gpu_numa_node(int device, std::string *cpulist) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  for (char *c = bus; *c; ++c) *c = (char)tolower(*c);
+  const std::string dir = std::string("/sys/bus/pci/devices/") + bus;
+  int node = -1;
+  if (FILE *f = fopen((dir + "/numa_node").c_str(), "r")) {
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+  }
+  if (cpulist) {
+    cpulist->clear();
+    if (FILE *f = fopen((dir + "/local_cpulist").c_str(), "r")) {
+      char buf[4096] = {0};
+      if (fgets(buf, sizeof buf, f)) *cpulist = buf;
+      fclose(f);
+    }
+  }
+  return node;
+}
+}  // namespace
+extern "C" {
+
+// Pinned host memory placed on the NUMA node of `device`'s PCIe root (best effort: the memory policy of the calling
+// thread is switched to "prefer that node" for the duration of the allocation; containers that forbid set_mempolicy
+// get a plain pinned allocation).  On a two-socket 8-GPU board uploads from the far socket cross the inter-socket link.
+void *lbm_host_alloc_near(size_t bytes, int device) {
+  const int node = gpu_numa_node(device, nullptr);
+  bool policy_set = false;
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1024 + 1) == 0;
+  }
+  void *p = lbm_host_alloc(bytes);
+  if (policy_set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+  return p;
+}
+
+// Restrict the calling thread to the CPUs local to `device` (sysfs local_cpulist).  Returns the NUMA node, or a
+// negative code when the topology is unknown or the affinity call is refused; purely an optimisation.
+int lbm_bind_thread_near(int device) {
+  std::string cpus;
+  const int node = gpu_numa_node(device, &cpus);
+  if (cpus.empty()) return fail(LBM_E_STATE, "no local_cpulist for GPU %d in sysfs", device);
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int count = 0;
+  const char *c = cpus.c_str();
+  while (*c) {  // "0-31,64-95"
+    char *end = nullptr;
+    long a = strtol(c, &end, 10), b = a;
+    if (end == c) break;
+    if (*end == '-') b = strtol(end + 1, &end, 10);
+    for (long k = a; k <= b && k < CPU_SETSIZE; ++k) { CPU_SET((int)k, &set); ++count; }
+    c = (*end == ',') ? end + 1 : end;
+    if (*end != ',') break;
+  }
+  if (!count) return fail(LBM_E_STATE, "empty local_cpulist for GPU %d", device);
+  if (sched_setaffinity(0, sizeof set, &set) != 0) return fail(LBM_E_STATE, "sched_setaffinity refused for GPU %d's CPUs", device);
+  return node >= 0 ? node : 0;
 }
 
 void *lbm_host_alloc(size_t bytes) {

@@ -109,3 +109,14 @@ def synthetic_obstacles(nx: int, ny: int, seed: int, solid_prob: float, row_begi
     return solid.astype(np.uint8)
 
 
+
+
+def perturbed_problem(nx: int, ny: int, iters: int, seed: int, solid_frac: float = 0.05):
+    """A seeded random test problem whose every halo row carries information from step 0 on: 5 % random solids and
+    every population perturbed by up to 10 % (shipped parameters otherwise).  Identical on every rank for one seed.
+    Used by the parity tests (tests/rank_worker.py) and by bench.py's driver-visible multi-GPU parity record."""
+    rng = np.random.default_rng(seed)
+    p = Params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    obst = (rng.random((ny, nx)) < solid_frac).astype(np.uint8)
+    cells = (initial_cells(p) * (1.0 + 0.1 * rng.random((ny, nx, 9))).astype(np.float32)).astype(np.float32)
+    return p, cells, obst

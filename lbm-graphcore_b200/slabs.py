@@ -8,7 +8,7 @@ ring) and only the populations that actually cross an edge travel:
     top owned row    -> planes NORTH_PLANES (2 N, 5 NE, 6 NW) -> south ghost row of the rank above
     bottom owned row -> planes SOUTH_PLANES (4 S, 7 SW, 8 SE) -> north ghost row of the rank below
 
-On the GPUs the sweep kernel itself performs those stores into peer memory (lbm_kernels.cuh, store_row_vec4);
+On the GPUs the sweep kernel itself performs those stores into peer memory (lbm_kernels.cuh, the `gn` / `gs` stores of sweep_tile_row);
 this module holds what the host has to agree on -- who owns which rows, who the ring neighbours are, how the
 IPC handles are exchanged and in which order the per-rank av_vels partials are combined -- so that bench.py,
 the tests and the gloo CPU model all use one definition.  `dist` is `torch.distributed` (any backend that
@@ -52,6 +52,24 @@ def connect_ring(solver, dist) -> None:
     dist.all_gather_object(blobs, solver.ipc_export())
     solver.ipc_connect(b"".join(blobs))
     dist.barrier()
+
+
+def close_ring(solver, dist) -> None:
+    """Two-phase teardown of a connected rank-mode solver (protocol in include/lbm_b200.h): all ranks have finished
+    their work -> every rank unmaps its neighbours' slabs -> barrier -> free.  Collective: every rank must call it."""
+    if dist is None or dist.get_world_size() == 1:
+        solver.close()
+        return
+    dist.barrier()           # nobody is still running or pushing halos
+    solver.ipc_disconnect()  # waits for this rank's stream, closes its peer mappings
+    dist.barrier()           # every mapping of every slab is closed
+    solver.close()
+
+
+def barrier_before_reupload(dist) -> None:
+    """A rank may reset its halo flags (lbm_upload / lbm_init_synthetic) only when no neighbour is still running."""
+    if dist is not None and dist.get_world_size() > 1:
+        dist.barrier()
 
 
 def combine_tot_u(dist, tot_u: np.ndarray, free_cells: int) -> tuple[np.ndarray, int]:

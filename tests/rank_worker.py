@@ -18,11 +18,7 @@ sys.path.insert(0, ROOT)
 
 def problem(lbm, nx, ny, iters, seed):
     """Same generator as tests/test_gpu_parity.py::_random_problem (seeded, identical on every rank)."""
-    rng = np.random.default_rng(seed)
-    p = lbm.Params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
-    obst = (rng.random((ny, nx)) < 0.05).astype(np.uint8)
-    cells = (lbm.initial_cells(p) * (1.0 + 0.1 * rng.random((ny, nx, 9))).astype(np.float32)).astype(np.float32)
-    return p, cells, obst
+    return lbm.perturbed_problem(nx, ny, iters, seed)
 
 
 def main():
@@ -55,8 +51,7 @@ def main():
     av = slabs.combine_av_vels(dist, tot, s.free_cells)
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), cells=got, row_begin=r0, tot_u=tot, free_cells=s.free_cells,
              av_vels=av, variant=s.kernel_variant)
-    dist.barrier()
-    s.close()
+    slabs.close_ring(s, dist)  # barrier -> unmap the neighbours -> barrier -> free
     dist.destroy_process_group()
 
 

@@ -114,10 +114,34 @@ def test_runner_cli_errors_before_any_gpu_work(lbm, tmp_path):
     assert r.returncode != 0 and "Could not parse obstacles file" in r.stderr
     r = run("--synthetic", "128x", "--iters", "5")
     assert r.returncode != 0
-    # the reference's flag spellings are accepted: --num-ipus, --device, --exe (the last two ignored)
+    # the reference's flag spellings are accepted: --num-ipus, --device (ignored), --exe (a prepared-solver file; one
+    # that does not exist yet means "prepare on the fly")
     r = run("--params=" + os.path.join(gold, "input_128x128.params"), "--obstacles=" + os.path.join(gold, "obstacles_128x128.dat"),
-            "--num-ipus", "1", "--device", "ipu", "--exe", "graph.exe", "--outdir", str(tmp_path), "--reruns", "0")
+            "--num-ipus", "1", "--device", "ipu", "--exe", str(tmp_path / "graph.exe"), "--outdir", str(tmp_path), "--reruns", "0")
     if lbm.device_count() == 0:
         assert r.returncode != 0 and "no CPU path" in r.stderr
     else:
         assert r.returncode == 0 and "==done==" in r.stdout
+
+
+def test_runner_accepts_the_cxxopts_spellings(lbm, tmp_path):
+    """What cxxopts 2.2 (the reference's parser, main/LbmRunner.cpp:14-33) accepts must parse here too: grouped short
+    flags (-dn 2), --flag=true/false, --name=value; GNU-style -n2 on top.  Parsing is judged by how far the run gets:
+    a parse error prints the usage, a good parse reaches the device check (or runs, on a GPU box)."""
+    gold = os.path.join(ROOT, "tests", "golden", "params")
+    files = ["--params", os.path.join(gold, "input_128x128.params"), "--obstacles", os.path.join(gold, "obstacles_128x128.dat"),
+             "--outdir", str(tmp_path), "--reruns", "0", "--iters", "10"]
+    run = lambda *a: subprocess.run([lbm.RUNNER_PATH, *files, *a], capture_output=True, text=True)
+    usage = "Runs a Lattice Boltzmann simulation"
+    for good in (["-dn", "1"], ["-n1"], ["-d", "-n", "1"], ["--debug=true"], ["--debug=false", "--num-gpus=1"], ["--debug=T"],
+                 ["-o", str(tmp_path / "state.lbm")], ["--stats"], ["--no-output=1"]):
+        r = run(*good)
+        assert usage not in r.stderr, (good, r.stderr)
+        if lbm.device_count() == 0:
+            assert r.returncode != 0 and "no CPU path" in r.stderr
+        else:
+            assert r.returncode == 0 and "==done==" in r.stdout, (good, r.stderr)
+            assert ("Capturing profile information" in r.stdout) == (good[0] in ("-dn", "-d", "--debug=true", "--debug=T"))
+    for bad in (["-nd", "1"], ["--debug=maybe"], ["-n"], ["--num-gpus"], ["-x"], ["stray"], ["--prepare"], ["-n", "two"]):
+        r = run(*bad)
+        assert r.returncode != 0 and usage in r.stderr, bad

@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 from conftest import ROOT
 
 
@@ -25,14 +27,28 @@ def test_reference_arm_line():
     base = line["cpu_baseline"]
     assert base["kind"] == "port" and base["cores"] >= 1 and base["value"] == line["value"] and "sample" in base
     assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 1 and line["vs_baseline"] is None
+    # the arm runs what it prints: W + K real timesteps of the WHOLE grid named in config, ms_per_step measured
+    assert "1 + 2 timesteps of the whole 512x512 grid" in base["sample"]
+    assert line["detail"]["rows_timed"] == 512
+    assert line["ms_per_step"] == pytest.approx(line["detail"]["timed_s"] * 1e3 / 2, rel=1e-2)
+    assert line["value"] == pytest.approx(512 * 512 / (line["ms_per_step"] * 1e-3) / 1e6, rel=2e-2)
+    # `config` describes the workload only (our arm prints the same object; run-specific facts live in `detail`)
+    assert set(line["config"]) == {"workload", "nx", "ny", "density", "accel", "omega", "seed", "solid_prob", "l2"}
+
+
+def test_both_arms_build_the_same_config_object():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = bench.workload_config("synthetic channel 16384x16384", 16384, 16384)
+    assert a["l2"].startswith("working set") and "no flush" in a["l2"]
+    assert bench.workload_config("x", 512, 512)["l2"].startswith("development override")
 
 
 def test_reference_arm_other_ranks_stay_silent():
     r = run_bench({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
     assert r.returncode == 0 and r.stdout.strip() == ""
-
-
-import pytest
 
 
 @pytest.mark.gpu
@@ -46,6 +62,10 @@ def test_our_arm_line_on_a_gpu():
     assert j["metric"] == "MLUPS" and j["unit"] == "MLUPS" and j["n_gpus"] == 1 and j["steps"] == 20 and j["warmup"] == 3
     assert j["dtype"] == "f32" and j["data"] == "synthetic" and j["higher_is_better"] is True and j["vs_baseline"] is None
     assert j["value"] > 1000 and j["ms_per_step"] > 0 and "workload" in j["config"]
+    assert set(j["config"]) == {"workload", "nx", "ny", "density", "accel", "omega", "seed", "solid_prob", "l2"}
+    assert set(j["detail"]) >= {"partition", "kernel_variant", "av_vels_last", "wall_ms_per_step"}
+    par = j["parity"]  # one GPU: the multi-slab kernel on two slabs sharing the GPU, and one slab, both against the oracle
+    assert par["ok"] and par["halo_lattice_sha_equal"] and par["one_slab_lattice_sha_equal"] and par["av_vels_max_ulp"] <= 1
     roof = j["roofline"]
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["peak"] > 1000
     assert roof["frac"] == pytest.approx(roof["achieved"] / roof["peak"], rel=1e-3)

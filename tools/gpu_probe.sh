@@ -8,7 +8,6 @@ for m in blob blobldg blobst; do
   run $m 16384 16384 128 4
   run $m 16384 16384 128 2
   run $m 16384 16384 256 4
-  run $m 16384 16384 64 8
 done
 run tile 16384 16384 128 4 3 3
 run tile 16384 16384 128 2 4 4
