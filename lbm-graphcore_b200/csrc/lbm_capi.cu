@@ -929,7 +929,7 @@ int build_graphs(lbm_handle *h, int parity) {
 }
 
 bool graphs_wanted(const lbm_handle *h, int iters) {
-  static const int env = getenv("LBM_B200_GRAPH") ? atoi(getenv("LBM_B200_GRAPH")) : -1;  // 0 off, 1 force, default auto
+  const int env = getenv("LBM_B200_GRAPH") ? atoi(getenv("LBM_B200_GRAPH")) : -1;  // 0 off, 1 force, default auto
   if (env == 0 || g_debug_sync || iters < kGraphSteps) return false;
   if (env == 1) return true;
   for (const Slab &s : h->slabs)

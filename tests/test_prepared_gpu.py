@@ -1,0 +1,122 @@
+"""Prepare once / run many (main/LbmPoplibs.cpp:375-389 serialises the solver, main/LbmRunner.cpp:20,75-84
+loads it with --exe): lbm_save / lbm_load must resume a run bit-exactly, the runner's --prepare / --exe / -o flags must
+produce the files of an uninterrupted run, and the time loop replayed from its cached CUDA graph must give the same bits
+as plain launches."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import obstacles_path, params_path, ulp_distance
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("nx,ny,first", [(384, 200, 25), (200, 70, 0), (1024, 64, 33)])
+def test_save_load_continue_equals_uninterrupted_run(oracle, lbm, tmp_path, nx, ny, first):
+    iters = 60
+    p, cells, obst = lbm.perturbed_problem(nx, ny, iters, seed=nx + ny)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    with lbm.Solver(p) as s:
+        s.upload(cells, obst)
+        s.run(iters)
+        straight_cells, straight_av = s.download()
+    path = str(tmp_path / "solver.lbm")
+    with lbm.Solver(p) as s:
+        s.upload(cells, obst)
+        s.run(first)
+        s.save(path)
+    assert os.path.getsize(path) > nx * ny * 37
+    with lbm.Solver.load(path) as s:
+        assert (s.params.nx, s.params.ny, s.params.max_iters) == (nx, ny, iters) and s.steps_done == first
+        assert s.free_cells == int((obst == 0).sum())
+        s.run(iters - first)
+        got_cells, got_av = s.download()
+    assert np.array_equal(_bits(got_cells), _bits(straight_cells)) and np.array_equal(_bits(got_cells), _bits(want_cells))
+    assert np.array_equal(_bits(got_av), _bits(straight_av))  # the steps done before the save come back bit for bit
+    assert ulp_distance(got_av, want_av).max() <= 1
+
+
+def test_load_rejects_garbage(lbm, tmp_path):
+    bad = tmp_path / "bad.lbm"
+    bad.write_bytes(b"not a solver" * 10)
+    with pytest.raises(lbm.LbmError, match="not a prepared-solver file"):
+        lbm.Solver.load(str(bad))
+    with pytest.raises(lbm.LbmError, match="cannot open"):
+        lbm.Solver.load(str(tmp_path / "missing.lbm"))
+    p, cells, obst = lbm.perturbed_problem(128, 16, 4, seed=1)
+    good = tmp_path / "good.lbm"
+    with lbm.Solver(p) as s:
+        s.upload(cells, obst)
+        s.save(str(good))
+    (tmp_path / "cut.lbm").write_bytes(good.read_bytes()[:-100])
+    with pytest.raises(lbm.LbmError, match="truncated"):
+        lbm.Solver.load(str(tmp_path / "cut.lbm"))
+
+
+@pytest.mark.parametrize("devices,nx,ny", [(None, 512, 300), ([0, 0, 0], 256, 90), (None, 200, 40)])
+def test_graph_replay_gives_the_same_bits_as_plain_launches(oracle, lbm, monkeypatch, devices, nx, ny):
+    """LBM_B200_GRAPH=1 forces the per-step time loop through its cached CUDA graph (16 steps per replay, the kernels
+    read the step number from device memory); the persistent kernel is switched off so the per-step path runs."""
+    iters = 70  # 16-step replays + a remainder of plain launches, in two lbm_run calls with different parities
+    p, cells, obst = lbm.perturbed_problem(nx, ny, iters, seed=7 * nx + ny)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    monkeypatch.setenv("LBM_B200_PERSISTENT", "0")
+    results = {}
+    for graph in ("0", "1"):
+        monkeypatch.setenv("LBM_B200_GRAPH", graph)
+        kw = {"devices": devices} if devices else {}
+        with lbm.Solver(p, **kw) as s:
+            s.upload(cells, obst)
+            n0 = s.launch_count
+            s.run(37)  # leaves an odd parity: the second call needs the other graph
+            s.run(33)
+            results[graph] = (*s.download(), s.launch_count - n0)
+    for graph in ("0", "1"):
+        got_cells, got_av, _ = results[graph]
+        assert np.array_equal(_bits(got_cells), _bits(want_cells)), f"graph={graph}"
+        assert ulp_distance(got_av, want_av).max() <= 1
+    assert np.array_equal(_bits(results["0"][1]), _bits(results["1"][1]))
+    assert results["1"][2] >= results["0"][2]  # replays are counted as the launches they stand for
+
+
+def test_runner_prepare_then_exe_and_resume(lbm, tmp_path):
+    """lbm_runner --prepare --exe F (the lbm_poplibs step) then lbm_runner --exe F: same output files as a plain run;
+    -o after half the steps then --exe for the rest: same files again (av_vels.dat covers all steps)."""
+    case, iters = "128x256", 3000
+    common = ["--params", params_path(case), "--obstacles", obstacles_path(case), "--reruns", "0"]
+    run = lambda *a: subprocess.run([lbm.RUNNER_PATH, *common, *a], capture_output=True, text=True, timeout=600)
+    plain = tmp_path / "plain"
+    plain.mkdir()
+    r = run("--outdir", str(plain), "--iters", str(iters))
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = str(tmp_path / "solver.exe")
+    r = run("--prepare", "--exe", exe)
+    assert r.returncode == 0 and "Serialising prepared solver" in r.stderr and os.path.exists(exe), r.stdout + r.stderr
+    via = tmp_path / "via_exe"
+    via.mkdir()
+    r = run("--exe", exe, "--outdir", str(via), "--iters", str(iters))
+    assert r.returncode == 0 and "Loading prepared solver to device" in r.stderr, r.stdout + r.stderr
+    for name in ("av_vels.dat", "final_state.dat"):
+        assert (via / name).read_bytes() == (plain / name).read_bytes(), name
+    half, rest = tmp_path / "half", tmp_path / "rest"
+    half.mkdir()
+    rest.mkdir()
+    state = str(tmp_path / "state.lbm")
+    r = run("--exe", exe, "--outdir", str(half), "--iters", "1700", "-o", state)
+    assert r.returncode == 0 and os.path.exists(state), r.stdout + r.stderr
+    r = run("--exe", state, "--outdir", str(rest), "--iters", str(iters - 1700))
+    assert r.returncode == 0, r.stdout + r.stderr
+    for name in ("av_vels.dat", "final_state.dat"):
+        assert (rest / name).read_bytes() == (plain / name).read_bytes(), name
+    # a prepared solver for another problem is refused
+    r = subprocess.run([lbm.RUNNER_PATH, "--params", params_path("128x128"), "--obstacles", obstacles_path("128x128"), "--exe", exe,
+                        "--outdir", str(rest), "--reruns", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "different problem" in r.stderr
