@@ -54,6 +54,9 @@ const bool g_debug_sync = getenv("LBM_B200_DEBUG_SYNC") != nullptr;
 
 constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation
 constexpr size_t kStageBytes = 64u << 20;  // AoS staging chunk for upload/download
+#ifndef LBM_CLUSTER_DEFAULT_CPT
+#define LBM_CLUSTER_DEFAULT_CPT 2  // cells per thread of the cluster-resident kernel (profiles/r02*_small_grids.txt)
+#endif
 constexpr int kPersistentMaxCtas = 1024;  // upper bound on the persistent kernel's grid
 constexpr size_t kPersistentPartials = 2 * (size_t)kPersistentMaxCtas * lbm::kTileH;
 constexpr size_t kPersistentMaxBytes = 96u << 20;  // both lattices must stay in the 126 MB L2 for the persistent kernel to pay
@@ -85,6 +88,14 @@ struct Slab {
   unsigned long long *barrier = nullptr;  // persistent kernel: grid-barrier arrivals since the last upload
   unsigned long long barrier_arrivals = 0;  // host copy of what *barrier holds when the queued launches have finished
   int persistent_grid = 0;     // > 0: the whole time loop runs as one cooperative launch of this many CTAs
+  // cluster-resident kernel (lattices in distributed shared memory): the smallest shipped inputs
+  int cluster_ctas = 0;        // > 0: the whole time loop runs as one launch of this many CTAs ...
+  int cluster_size = 0;        // ... in clusters of this many
+  int cluster_cells = 0, cluster_cpt = 0;  // cells per CTA / per thread
+  bool cluster_refused = false;  // a launch failed: do not try again
+  float *cluster_halo = nullptr;
+  int *cluster_flags = nullptr;
+  double *cluster_tot = nullptr;
   unsigned long long *free_dev = nullptr;
   float *stage = nullptr;
   // neighbours (own pointers when there is a single slab)
@@ -144,6 +155,29 @@ namespace {
 
 size_t blob_bytes() { return sizeof(cudaIpcMemHandle_t) + 4 * sizeof(int); }
 
+// the instantiations of sweep_cluster_kernel: (nx, cells per CTA, cells per thread)
+const void *cluster_kernel(int nx, int cells, int cpt) {
+#define LBM_CK(NX, CELLS, CPT) \
+  if (nx == NX && cells == CELLS && cpt == CPT) return (const void *)lbm::sweep_cluster_kernel<NX, CELLS, CPT>;
+  LBM_CK(128, 1024, 4) LBM_CK(128, 1024, 2) LBM_CK(128, 512, 4) LBM_CK(128, 512, 2) LBM_CK(128, 512, 1)
+  LBM_CK(256, 1024, 4) LBM_CK(256, 1024, 2) LBM_CK(256, 512, 4) LBM_CK(256, 512, 2) LBM_CK(256, 512, 1)
+#undef LBM_CK
+  return nullptr;
+}
+void cluster_launch_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, int nx, int cells, int cpt, int ctas, int cs,
+                           cudaStream_t stream) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3((unsigned)ctas, 1, 1);
+  cfg.blockDim = dim3((unsigned)lbm::cluster_threads(cells, cpt), 1, 1);
+  cfg.dynamicSmemBytes = lbm::cluster_smem_bytes(nx, cells);
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+}
+
 // Choose the sweep kernel and its launch shape for one slab: one CTA of 8 warps per 128 x 8 tile.
 int configure_launch(lbm_handle *h, Slab &s) {
   s.kernel = (h->nx % lbm::kTileW == 0) ? KERNEL_VEC4 : (h->nx > lbm::kTileW ? KERNEL_HYBRID : KERNEL_SCALAR);
@@ -169,6 +203,60 @@ int configure_launch(lbm_handle *h, Slab &s) {
       int ctas = std::min(std::min(LBM_PERSIST_MINB * sms, kPersistentMaxCtas), units);
       if (const char *e = getenv("LBM_B200_PERSIST_CTAS")) ctas = std::max(1, std::min(atoi(e), ctas));
       s.persistent_grid = ctas;
+    }
+  }
+  // The smallest inputs (nx = 128 or 256, a few dozen K cells) keep both lattices in the distributed shared memory of
+  // thread-block clusters (sweep_cluster_kernel): CTAs of 512 cells (1024 when that many CTAs cannot be co-resident),
+  // the largest cluster size <= 16 that divides the CTA count.  LBM_B200_CLUSTER=0 disables; LBM_B200_CLUSTER_CELLS /
+  // _CPT / _SIZE pin the shape (tuning runs).
+  s.cluster_ctas = 0;
+  const int want_cluster = getenv("LBM_B200_CLUSTER") ? atoi(getenv("LBM_B200_CLUSTER")) : 1;
+  if (!h->multi && want_cluster != 0 && want == -1 && !getenv("LBM_B200_KERNEL") && !s.cluster_refused &&
+      (h->nx == 128 || h->nx == 256)) {
+    CUDA_TRY(cudaSetDevice(s.device));
+    const int env_cells = getenv("LBM_B200_CLUSTER_CELLS") ? atoi(getenv("LBM_B200_CLUSTER_CELLS")) : 0;
+    const int env_cpt = getenv("LBM_B200_CLUSTER_CPT") ? atoi(getenv("LBM_B200_CLUSTER_CPT")) : 0;
+    const int env_cs = getenv("LBM_B200_CLUSTER_SIZE") ? atoi(getenv("LBM_B200_CLUSTER_SIZE")) : 0;
+    for (int cells : {512, 1024}) {
+      if (s.cluster_ctas > 0) break;
+      if (env_cells && env_cells != cells) continue;
+      const int rows = cells / h->nx, cpt = env_cpt ? env_cpt : LBM_CLUSTER_DEFAULT_CPT;
+      if (rows < 2 || s.nyl % rows != 0) continue;
+      const int G = s.nyl / rows;
+      const void *fn = cluster_kernel(h->nx, cells, cpt);
+      if (!fn) continue;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbm::cluster_smem_bytes(h->nx, cells)) != cudaSuccess ||
+          cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      for (int cs = lbm::kClusterMaxSize; cs >= 1; --cs) {  // the largest cluster that divides the grid and fits
+        if (G % cs != 0 || (env_cs && env_cs != cs)) continue;
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr[1];
+        cluster_launch_config(cfg, attr, h->nx, cells, cpt, G, cs, s.stream);
+        int active = 0;
+        if (cudaOccupancyMaxActiveClusters(&active, fn, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (active * cs < G) continue;  // the clusters wait for each other: all of them must be resident
+        s.cluster_ctas = G;
+        s.cluster_size = cs;
+        s.cluster_cells = cells;
+        s.cluster_cpt = cpt;
+        break;
+      }
+    }
+    cudaGetLastError();
+    if (s.cluster_ctas > 0) {
+      // (re)allocate for this shape: halo rows and flags per CTA, one total per cluster and step
+      cudaFree(s.cluster_halo); cudaFree(s.cluster_flags); cudaFree(s.cluster_tot);
+      s.cluster_halo = nullptr; s.cluster_flags = nullptr; s.cluster_tot = nullptr;
+      const size_t halo_floats = (size_t)2 * s.cluster_ctas * 2 * 3 * h->nx;
+      CUDA_TRY(cudaMalloc((void **)&s.cluster_halo, halo_floats * sizeof(float)));
+      CUDA_TRY(cudaMalloc((void **)&s.cluster_flags, (size_t)s.cluster_ctas * 2 * lbm::kClusterSegs * sizeof(int)));
+      CUDA_TRY(cudaMemset(s.cluster_flags, 0, (size_t)s.cluster_ctas * 2 * lbm::kClusterSegs * sizeof(int)));
+      CUDA_TRY(cudaMalloc((void **)&s.cluster_tot,
+                          (size_t)std::max(h->max_iters, 1) * (s.cluster_ctas / s.cluster_size) * sizeof(double)));
+      s.persistent_grid = 0;
     }
   }
   return LBM_OK;
@@ -221,6 +309,9 @@ void free_slab(Slab &s) {
     if (s.drained[b]) cudaEventDestroy(s.drained[b]);
   }
   if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+  cudaFree(s.cluster_tot);
+  cudaFree(s.cluster_flags);
+  cudaFree(s.cluster_halo);
   cudaFree(s.stage);
   cudaFree(s.free_dev);
   cudaFree(s.step);
@@ -373,6 +464,42 @@ int launch_persistent(lbm_handle *h, Slab &s, int iters) {
   return LBM_OK;
 }
 
+// The whole time loop of a single tiny slab as one launch of thread-block clusters that keep the lattices in shared memory.
+int launch_cluster(lbm_handle *h, Slab &s, int iters) {
+  lbm::ClusterArgs a{};
+  a.lattice = s.buf[h->cur];
+  a.mask = s.mask;
+  a.halo = s.cluster_halo;
+  a.flags = s.cluster_flags;
+  a.cluster_tot = s.cluster_tot;
+  a.error = s.step + 1;
+  a.ntx = h->ntx;
+  a.ny = h->ny;
+  a.accel_row = h->ny - 2;
+  a.omega = h->omega;
+  a.one_minus_omega = 1 - h->omega;
+  a.w1 = h->density * h->accel / 9.f;
+  a.w2 = h->density * h->accel / 36.f;
+  a.t0 = h->steps_done;
+  a.steps = iters;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  cluster_launch_config(cfg, attr, h->nx, s.cluster_cells, s.cluster_cpt, s.cluster_ctas, s.cluster_size, s.stream);
+  void *args[] = {&a};
+  cudaError_t e = cudaLaunchKernelExC(&cfg, cluster_kernel(h->nx, s.cluster_cells, s.cluster_cpt), args);
+  if (e != cudaSuccess) {  // not launchable here after all: fall back to the other paths for good
+    cudaGetLastError();
+    s.cluster_ctas = 0;
+    s.cluster_refused = true;
+    return LBM_OK;
+  }
+  const int clusters = s.cluster_ctas / s.cluster_size;
+  lbm::reduce_clusters_kernel<<<(iters + 255) / 256, 256, 0, s.stream>>>(s.cluster_tot, s.tot_u, clusters, h->steps_done, iters);
+  h->launches += 2;
+  KERNEL_CHECK(s.stream, "sweep_cluster/reduce_clusters");
+  return LBM_OK;
+}
+
 // ---- staged host <-> device pipelines -------------------------------------------------------------
 // Rows travel in chunks through the two halves of the slab's staging buffer.  `chunk` counts chunks since the last
 // drain so that consecutive pipelines (cells, then obstacles) keep alternating halves correctly.
@@ -466,6 +593,8 @@ int reset_counters(lbm_handle *h) {
     s.barrier_arrivals = 0;
     CUDA_TRY(cudaMemsetAsync(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.free_dev, 0, sizeof(unsigned long long), s.stream));
+    if (s.cluster_flags)
+      CUDA_TRY(cudaMemsetAsync(s.cluster_flags, 0, (size_t)s.cluster_ctas * 2 * lbm::kClusterSegs * sizeof(int), s.stream));
   }
   h->cur = 0;
   h->steps_done = 0;
@@ -947,9 +1076,10 @@ int lbm_run(lbm_handle *h, int iters) {
   if (iters < 0 || h->steps_done + iters > h->max_iters)
     return fail(LBM_E_ARG, "cannot run %d more steps: %d of max_iters=%d already done", iters, h->steps_done,
                 h->max_iters);
-  const bool persistent = h->slabs.size() == 1 && h->slabs[0].persistent_grid > 0 && iters > 0;
+  const bool clustered = h->slabs.size() == 1 && h->slabs[0].cluster_ctas > 0 && iters > 0;
+  const bool persistent = !clustered && h->slabs.size() == 1 && h->slabs[0].persistent_grid > 0 && iters > 0;
   // build (once) the replayable time loop before the timed region starts
-  const bool use_graphs = !persistent && graphs_wanted(h, iters);
+  const bool use_graphs = !persistent && !clustered && graphs_wanted(h, iters);
   if (use_graphs && h->graph_state[h->cur] == 0) {
     int rc = build_graphs(h, h->cur);
     if (rc) return rc;
@@ -973,7 +1103,22 @@ int lbm_run(lbm_handle *h, int iters) {
     }
     h->first_run_pending = false;
   }
-  if (h->halo_pending) {
+  if (clustered) {
+    // a single tiny slab: the lattices move into the shared memory of thread-block clusters for the whole call.  The
+    // kernel works on the owned rows only (y wraps by index), so the HBM ghost rows are stale afterwards.
+    Slab &s = h->slabs[0];
+    int rc = launch_cluster(h, s, iters);
+    if (rc) return rc;
+    if (s.cluster_ctas > 0) {
+      iters_left_for_loop = 0;
+      h->halo_pending = true;
+    } else {
+      rc = configure_launch(h, s);  // the launch was refused: pick the persistent / per-step path instead
+      if (rc) return rc;
+    }
+  }
+  const bool persistent_now = iters_left_for_loop > 0 && h->slabs.size() == 1 && h->slabs[0].persistent_grid > 0;
+  if (h->halo_pending && iters_left_for_loop > 0) {
     // ... then the initial halo of a fresh (or re-loaded) lattice: every slab fills its neighbours' ghost rows and
     // publishes the epoch the next timestep waits for
     for (Slab &s : h->slabs) {
@@ -989,7 +1134,7 @@ int lbm_run(lbm_handle *h, int iters) {
     }
     h->halo_pending = false;
   }
-  if (persistent) {
+  if (persistent_now) {
     // a single small slab: the whole time loop is one cooperative launch
     Slab &s = h->slabs[0];
     int rc = launch_persistent(h, s, iters);
@@ -1259,6 +1404,7 @@ int lbm_launch_count(lbm_handle *h, long long *count) {
 }
 const char *lbm_kernel_variant(lbm_handle *h) {
   if (!h || h->slabs.empty()) return "";
+  if (h->slabs[0].cluster_ctas > 0) return "vec4-cluster";
   switch (h->slabs[0].kernel) {
     case KERNEL_VEC4: return h->slabs[0].persistent_grid > 0 ? "vec4-persistent" : "vec4";
     case KERNEL_HYBRID: return h->slabs[0].persistent_grid > 0 ? "hybrid-persistent" : "hybrid";

@@ -45,7 +45,7 @@ def test_shipped_inputs_bit_exact_short(oracle, lbm, case):
     obst = lbm.load_obstacles(p.nx, p.ny, obstacles_path(case))
     assert np.array_equal(obst, oracle.load_obstacles(obstacles_path(case), p.nx, p.ny))
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == "vec4-persistent"  # fits in L2: the whole time loop is one cooperative launch
+        assert s.kernel_variant == "vec4-cluster"  # 16 K / 32 K cells: the lattices live in cluster shared memory
     _assert_matches_oracle(oracle, lbm, p, op, lbm.initial_cells(p), obst, 1500)
 
 
