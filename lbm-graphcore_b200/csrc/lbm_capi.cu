@@ -54,9 +54,7 @@ const bool g_debug_sync = getenv("LBM_B200_DEBUG_SYNC") != nullptr;
 
 constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation
 constexpr size_t kStageBytes = 64u << 20;  // AoS staging chunk for upload/download
-#ifndef LBM_CLUSTER_DEFAULT_CPT
-#define LBM_CLUSTER_DEFAULT_CPT 2  // cells per thread of the cluster-resident kernel (profiles/r02*_small_grids.txt)
-#endif
+constexpr int kClusterChunkSteps = 8192;  // timesteps per launch of the cluster-resident kernel
 constexpr int kPersistentMaxCtas = 1024;  // upper bound on the persistent kernel's grid
 constexpr size_t kPersistentPartials = 2 * (size_t)kPersistentMaxCtas * lbm::kTileH;
 constexpr size_t kPersistentMaxBytes = 96u << 20;  // both lattices must stay in the 126 MB L2 for the persistent kernel to pay
@@ -93,9 +91,9 @@ struct Slab {
   int cluster_size = 0;        // ... in clusters of this many
   int cluster_cells = 0, cluster_cpt = 0;  // cells per CTA / per thread
   bool cluster_refused = false;  // a launch failed: do not try again
-  float *cluster_halo = nullptr;
-  int *cluster_flags = nullptr;
-  double *cluster_tot = nullptr;
+  uint2 *cluster_halo = nullptr;   // tagged packets of the edge rows that cross a cluster boundary
+  size_t cluster_halo_bytes = 0;
+  double *cluster_tot = nullptr;   // [kClusterChunkSteps][cluster_ctas] CTA partials of one launch
   unsigned long long *free_dev = nullptr;
   float *stage = nullptr;
   // neighbours (own pointers when there is a single slab)
@@ -159,7 +157,7 @@ size_t blob_bytes() { return sizeof(cudaIpcMemHandle_t) + 4 * sizeof(int); }
 const void *cluster_kernel(int nx, int cells, int cpt) {
 #define LBM_CK(NX, CELLS, CPT) \
   if (nx == NX && cells == CELLS && cpt == CPT) return (const void *)lbm::sweep_cluster_kernel<NX, CELLS, CPT>;
-  LBM_CK(128, 1024, 4) LBM_CK(128, 1024, 2) LBM_CK(128, 512, 4) LBM_CK(128, 512, 2) LBM_CK(128, 512, 1)
+  LBM_CK(128, 1024, 4) LBM_CK(128, 1024, 2) LBM_CK(128, 512, 4) LBM_CK(128, 512, 2) LBM_CK(128, 512, 1) LBM_CK(128, 256, 1)
   LBM_CK(256, 1024, 4) LBM_CK(256, 1024, 2) LBM_CK(256, 512, 4) LBM_CK(256, 512, 2) LBM_CK(256, 512, 1)
 #undef LBM_CK
   return nullptr;
@@ -206,8 +204,8 @@ int configure_launch(lbm_handle *h, Slab &s) {
     }
   }
   // The smallest inputs (nx = 128 or 256, a few dozen K cells) keep both lattices in the distributed shared memory of
-  // thread-block clusters (sweep_cluster_kernel): CTAs of 512 cells (1024 when that many CTAs cannot be co-resident),
-  // the largest cluster size <= 16 that divides the CTA count.  LBM_B200_CLUSTER=0 disables; LBM_B200_CLUSTER_CELLS /
+  // thread-block clusters (sweep_cluster_kernel): CTAs of 256, 512 or 1024 cells -- the smallest whose CTAs can all be
+  // co-resident -- one cell per thread (two at 1024), the largest cluster size <= 16 that divides the CTA count and fits.  LBM_B200_CLUSTER=0 disables; LBM_B200_CLUSTER_CELLS /
   // _CPT / _SIZE pin the shape (tuning runs).
   s.cluster_ctas = 0;
   const int want_cluster = getenv("LBM_B200_CLUSTER") ? atoi(getenv("LBM_B200_CLUSTER")) : 1;
@@ -217,10 +215,12 @@ int configure_launch(lbm_handle *h, Slab &s) {
     const int env_cells = getenv("LBM_B200_CLUSTER_CELLS") ? atoi(getenv("LBM_B200_CLUSTER_CELLS")) : 0;
     const int env_cpt = getenv("LBM_B200_CLUSTER_CPT") ? atoi(getenv("LBM_B200_CLUSTER_CPT")) : 0;
     const int env_cs = getenv("LBM_B200_CLUSTER_SIZE") ? atoi(getenv("LBM_B200_CLUSTER_SIZE")) : 0;
-    for (int cells : {512, 1024}) {
+    // smallest CTAs first: the update is issue-bound per SM, so the more SMs share a lattice the shorter a step
+    // (profiles/r02b_small_grids_cluster_v3.txt: 128^2 1.31 / 0.86 us per step with 1024 / 512 cells per CTA)
+    for (int cells : {256, 512, 1024}) {
       if (s.cluster_ctas > 0) break;
       if (env_cells && env_cells != cells) continue;
-      const int rows = cells / h->nx, cpt = env_cpt ? env_cpt : LBM_CLUSTER_DEFAULT_CPT;
+      const int rows = cells / h->nx, cpt = env_cpt ? env_cpt : (cells == 1024 ? 2 : 1);
       if (rows < 2 || s.nyl % rows != 0) continue;
       const int G = s.nyl / rows;
       const void *fn = cluster_kernel(h->nx, cells, cpt);
@@ -247,15 +247,13 @@ int configure_launch(lbm_handle *h, Slab &s) {
     }
     cudaGetLastError();
     if (s.cluster_ctas > 0) {
-      // (re)allocate for this shape: halo rows and flags per CTA, one total per cluster and step
-      cudaFree(s.cluster_halo); cudaFree(s.cluster_flags); cudaFree(s.cluster_tot);
-      s.cluster_halo = nullptr; s.cluster_flags = nullptr; s.cluster_tot = nullptr;
-      const size_t halo_floats = (size_t)2 * s.cluster_ctas * 2 * 3 * h->nx;
-      CUDA_TRY(cudaMalloc((void **)&s.cluster_halo, halo_floats * sizeof(float)));
-      CUDA_TRY(cudaMalloc((void **)&s.cluster_flags, (size_t)s.cluster_ctas * 2 * lbm::kClusterSegs * sizeof(int)));
-      CUDA_TRY(cudaMemset(s.cluster_flags, 0, (size_t)s.cluster_ctas * 2 * lbm::kClusterSegs * sizeof(int)));
-      CUDA_TRY(cudaMalloc((void **)&s.cluster_tot,
-                          (size_t)std::max(h->max_iters, 1) * (s.cluster_ctas / s.cluster_size) * sizeof(double)));
+      // (re)allocate for this shape: halo packets per CTA, one partial per CTA and step of a launch
+      cudaFree(s.cluster_halo); cudaFree(s.cluster_tot);
+      s.cluster_halo = nullptr; s.cluster_tot = nullptr;
+      s.cluster_halo_bytes = (size_t)2 * s.cluster_ctas * 2 * 3 * h->nx * sizeof(uint2);
+      CUDA_TRY(cudaMalloc((void **)&s.cluster_halo, s.cluster_halo_bytes));
+      CUDA_TRY(cudaMemset(s.cluster_halo, 0, s.cluster_halo_bytes));
+      CUDA_TRY(cudaMalloc((void **)&s.cluster_tot, (size_t)kClusterChunkSteps * s.cluster_ctas * sizeof(double)));
       s.persistent_grid = 0;
     }
   }
@@ -310,7 +308,6 @@ void free_slab(Slab &s) {
   }
   if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
   cudaFree(s.cluster_tot);
-  cudaFree(s.cluster_flags);
   cudaFree(s.cluster_halo);
   cudaFree(s.stage);
   cudaFree(s.free_dev);
@@ -464,14 +461,14 @@ int launch_persistent(lbm_handle *h, Slab &s, int iters) {
   return LBM_OK;
 }
 
-// The whole time loop of a single tiny slab as one launch of thread-block clusters that keep the lattices in shared memory.
+// The time loop of a single tiny slab as launches of thread-block clusters that keep the lattices in shared memory
+// (kClusterChunkSteps timesteps per launch: the per-step CTA partials of one launch wait in s.cluster_tot).
 int launch_cluster(lbm_handle *h, Slab &s, int iters) {
   lbm::ClusterArgs a{};
   a.lattice = s.buf[h->cur];
   a.mask = s.mask;
   a.halo = s.cluster_halo;
-  a.flags = s.cluster_flags;
-  a.cluster_tot = s.cluster_tot;
+  a.cta_tot = s.cluster_tot;
   a.error = s.step + 1;
   a.ntx = h->ntx;
   a.ny = h->ny;
@@ -480,23 +477,26 @@ int launch_cluster(lbm_handle *h, Slab &s, int iters) {
   a.one_minus_omega = 1 - h->omega;
   a.w1 = h->density * h->accel / 9.f;
   a.w2 = h->density * h->accel / 36.f;
-  a.t0 = h->steps_done;
-  a.steps = iters;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   cluster_launch_config(cfg, attr, h->nx, s.cluster_cells, s.cluster_cpt, s.cluster_ctas, s.cluster_size, s.stream);
-  void *args[] = {&a};
-  cudaError_t e = cudaLaunchKernelExC(&cfg, cluster_kernel(h->nx, s.cluster_cells, s.cluster_cpt), args);
-  if (e != cudaSuccess) {  // not launchable here after all: fall back to the other paths for good
-    cudaGetLastError();
-    s.cluster_ctas = 0;
-    s.cluster_refused = true;
-    return LBM_OK;
+  const void *fn = cluster_kernel(h->nx, s.cluster_cells, s.cluster_cpt);
+  for (int done = 0; done < iters; done += kClusterChunkSteps) {
+    a.t0 = h->steps_done + done;
+    a.steps = std::min(kClusterChunkSteps, iters - done);
+    void *args[] = {&a};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      if (done > 0) return fail(LBM_E_CUDA, "cluster launch failed mid-run: %s", cudaGetErrorString(e));
+      s.cluster_ctas = 0;  // not launchable here after all: fall back to the other paths for good
+      s.cluster_refused = true;
+      return LBM_OK;
+    }
+    lbm::reduce_ctas_kernel<<<(a.steps + 255) / 256, 256, 0, s.stream>>>(s.cluster_tot, s.tot_u, s.cluster_ctas, a.t0, a.steps);
+    h->launches += 2;
+    KERNEL_CHECK(s.stream, "sweep_cluster/reduce_ctas");
   }
-  const int clusters = s.cluster_ctas / s.cluster_size;
-  lbm::reduce_clusters_kernel<<<(iters + 255) / 256, 256, 0, s.stream>>>(s.cluster_tot, s.tot_u, clusters, h->steps_done, iters);
-  h->launches += 2;
-  KERNEL_CHECK(s.stream, "sweep_cluster/reduce_clusters");
   return LBM_OK;
 }
 
@@ -593,8 +593,7 @@ int reset_counters(lbm_handle *h) {
     s.barrier_arrivals = 0;
     CUDA_TRY(cudaMemsetAsync(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double), s.stream));
     CUDA_TRY(cudaMemsetAsync(s.free_dev, 0, sizeof(unsigned long long), s.stream));
-    if (s.cluster_flags)
-      CUDA_TRY(cudaMemsetAsync(s.cluster_flags, 0, (size_t)s.cluster_ctas * 2 * lbm::kClusterSegs * sizeof(int), s.stream));
+    if (s.cluster_halo) CUDA_TRY(cudaMemsetAsync(s.cluster_halo, 0, s.cluster_halo_bytes, s.stream));  // packet tags restart at 0
   }
   h->cur = 0;
   h->steps_done = 0;

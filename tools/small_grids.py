@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 CASES = {"128x128": 20000, "128x256": 20000, "256x256": 20000, "1024x1024": 5000}
 VARIANTS = [("cluster", {})]
 VARIANTS += [(f"cluster_{cells}x{cpt}", {"LBM_B200_CLUSTER_CELLS": str(cells), "LBM_B200_CLUSTER_CPT": str(cpt)})
-             for cells, cpt in ((1024, 4), (1024, 2), (512, 4), (512, 2), (512, 1))]
+             for cells, cpt in ((1024, 2), (512, 2), (512, 1), (256, 1))]
 VARIANTS += [("cluster_cs8", {"LBM_B200_CLUSTER_SIZE": "8"}),
              ("persistent", {"LBM_B200_CLUSTER": "0"}), ("perstep", {"LBM_B200_PERSISTENT": "0", "LBM_B200_GRAPH": "0"}),
              ("perstep_graph", {"LBM_B200_PERSISTENT": "0", "LBM_B200_GRAPH": "1"})]
