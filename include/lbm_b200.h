@@ -109,6 +109,22 @@ const char *lbm_kernel_variant(lbm_handle *h);
 int lbm_create_on_devices(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel,
                           float omega, int num_slabs, const int *devices);
 
+/* 2-D block partition (what the reference does across IPUs: main/include/StructuredGridUtils.hpp:501-527 cuts the grid
+ * for 8 devices into 4 x 2 or 2 x 4 blocks, :805-851 gives every block a one-cell halo with wrap-around).  The grid is
+ * cut into px columns x py rows of blocks; block (bx, by) -- index by * px + bx, GPU devices[index] (NULL: GPU = index; a
+ * device may repeat, as in lbm_create_on_devices) -- owns columns [bx*nx/px, (bx+1)*nx/px) and rows [by*ny/py,
+ * (by+1)*ny/py).  Besides the ghost rows of the row-slab partition every block keeps a west and an east ghost column and
+ * four corner ghosts; the sweep kernel of the block that computes an edge cell stores its outgoing populations straight
+ * into the ghost cells of the (up to eight) neighbouring blocks, over NVLink when they live on another GPU, with one
+ * epoch flag per neighbour.  Everything else (upload, run, download, save) behaves as for lbm_create. */
+int lbm_create_grid(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel, float omega, int px,
+                    int py, const int *devices);
+/* blocks per row / per column of the partition (1 x slabs for row slabs) */
+int lbm_partition(lbm_handle *h, int *px, int *py);
+/* like lbm_slab_info, with the block's columns as well */
+int lbm_block_info(lbm_handle *h, int block, int *device, int *row_begin, int *row_count, int *col_begin, int *col_count,
+                   long long *free_cells);
+
 /* Generate the synthetic channel of SURVEY.md 8(d) on the device instead of uploading it: solid rows 0
  * and ny-1, i.i.d. solids with probability `solid_prob` elsewhere except on the driven row ny-2,
  * decided by splitmix64(seed + y*nx + x); cells get Cells::initialise values

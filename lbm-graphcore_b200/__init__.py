@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_host_alloc_near", "lbm_bind_thread_near", "lbm_create_rank", "lbm_ipc_blob_bytes",
-    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_problem", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
+    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_problem", "lbm_create_grid", "lbm_partition", "lbm_block_info", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
 )
 
 
@@ -91,6 +91,9 @@ def _load() -> ctypes.CDLL:
     lib.lbm_ipc_export.argtypes = [c_void_p, c_void_p]
     lib.lbm_ipc_connect.argtypes = [c_void_p, c_void_p]
     lib.lbm_ipc_disconnect.argtypes = [c_void_p]
+    lib.lbm_create_grid.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_int, P(c_int)]
+    lib.lbm_partition.argtypes = [c_void_p, P(c_int), P(c_int)]
+    lib.lbm_block_info.argtypes = [c_void_p, c_int, P(c_int), P(c_int), P(c_int), P(c_int), P(c_int), P(ctypes.c_longlong)]
     lib.lbm_save.argtypes = [c_void_p, ctypes.c_char_p]
     lib.lbm_load.argtypes = [P(c_void_p), ctypes.c_char_p, c_int]
     lib.lbm_problem.argtypes = [c_void_p, P(c_int), P(c_int), P(c_int), P(c_float), P(c_float), P(c_float)]
@@ -138,12 +141,17 @@ class Solver:
     ``lbm_create_on_devices``; ``rank``/``world`` select the one-process-per-GPU mode."""
 
     def __init__(self, params: Params, num_gpus: int = 1, devices: list[int] | None = None,
-                 rank: int | None = None, world: int | None = None, device: int = 0):
+                 rank: int | None = None, world: int | None = None, device: int = 0,
+                 grid: tuple[int, int] | None = None):
         self.params = params
         self._h = ctypes.c_void_p()
         p = params
         args = (p.nx, p.ny, p.max_iters, p.density, p.accel, p.omega)
-        if rank is not None:
+        if grid is not None:  # (px, py) blocks; devices = GPU of block by * px + bx (default: one GPU each)
+            px, py = grid
+            arr = (ctypes.c_int * (px * py))(*devices) if devices is not None else None
+            _check(lib.lbm_create_grid(ctypes.byref(self._h), *args, px, py, arr))
+        elif rank is not None:
             _check(lib.lbm_create_rank(ctypes.byref(self._h), *args, rank, world, device))
         elif devices is not None:
             arr = (ctypes.c_int * len(devices))(*devices)
@@ -269,6 +277,27 @@ class Solver:
             _check(lib.lbm_slab_info(self._h, i, ctypes.byref(d), ctypes.byref(r0), ctypes.byref(rc), ctypes.byref(fc)))
             out.append({"device": d.value, "row_begin": r0.value, "row_count": rc.value, "free_cells": fc.value})
         return out
+
+    @property
+    def blocks(self) -> list[dict]:
+        """Per block of the partition: GPU, global rows and columns, non-obstacle cells (lbm_block_info)."""
+        n = ctypes.c_int()
+        _check(lib.lbm_slab_count(self._h, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            d, r0, rc, c0, cc, fc = (ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(),
+                                     ctypes.c_longlong())
+            _check(lib.lbm_block_info(self._h, i, ctypes.byref(d), ctypes.byref(r0), ctypes.byref(rc), ctypes.byref(c0),
+                                      ctypes.byref(cc), ctypes.byref(fc)))
+            out.append({"device": d.value, "row_begin": r0.value, "row_count": rc.value, "col_begin": c0.value,
+                        "col_count": cc.value, "free_cells": fc.value})
+        return out
+
+    @property
+    def partition(self) -> tuple[int, int]:
+        px, py = ctypes.c_int(), ctypes.c_int()
+        _check(lib.lbm_partition(self._h, ctypes.byref(px), ctypes.byref(py)))
+        return px.value, py.value
 
     @property
     def kernel_variant(self) -> str:

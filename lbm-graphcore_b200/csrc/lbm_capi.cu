@@ -63,6 +63,9 @@ struct Slab {
   int device = 0;
   int row0 = 0;  // first owned global row
   int nyl = 0;   // owned rows
+  int col0 = 0;  // first owned global column (0 unless the grid is cut into 2-D blocks)
+  int nxl = 0;   // owned columns (nx for a row slab)
+  int ntx_sweep = 0;  // tile columns that hold owned cells = ceil(nxl / 128)
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
   // upload/download pipeline: the staging buffer is used as two halves; PCIe copies run on copy_stream while the
@@ -102,6 +105,9 @@ struct Slab {
   int *flag_to_south = nullptr;
   int *flag_to_north = nullptr;
   int south_ghost_row = 0;
+  // 2-D blocks: the six further neighbours (lbm::SIDE_W .. SIDE_NE), own pointers where the partition wraps onto itself
+  float *side_buf[6][2] = {};
+  int *flag_to_side[6] = {};
   // launch configuration
   int kernel = 0;  // KERNEL_SCALAR / KERNEL_VEC4 / KERNEL_HYBRID
   int tiles_y = 1; // tile rows this slab sweeps = ceil((nyl + 2) / 8)
@@ -131,7 +137,9 @@ struct lbm_handle {
   size_t lattice_floats = 0;
   size_t lattice_bytes = 0;
   std::vector<Slab> slabs;
-  bool multi = false;      // more than one slab in the ring
+  bool multi = false;      // more than one slab in the ring (or a 2-D block partition): flags and halo pushes are on
+  bool xghost = false;     // 2-D block partition: blocks keep ghost columns (lbm_create_grid)
+  int px = 1, py = 1;      // blocks per row / per column of the partition (1 x slabs for row slabs)
   bool rank_mode = false;  // one process per GPU
   int rank = 0, world = 1;
   bool connected = false;
@@ -178,12 +186,12 @@ void cluster_launch_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, i
 
 // Choose the sweep kernel and its launch shape for one slab: one CTA of 8 warps per 128 x 8 tile.
 int configure_launch(lbm_handle *h, Slab &s) {
-  s.kernel = (h->nx % lbm::kTileW == 0) ? KERNEL_VEC4 : (h->nx > lbm::kTileW ? KERNEL_HYBRID : KERNEL_SCALAR);
+  s.kernel = (s.nxl % lbm::kTileW == 0) ? KERNEL_VEC4 : (s.nxl > lbm::kTileW ? KERNEL_HYBRID : KERNEL_SCALAR);
   // development knob (parity tests of the scalar path on vectorisable sizes)
   if (const char *e = getenv("LBM_B200_KERNEL"))
     if (!strcmp(e, "scalar")) s.kernel = KERNEL_SCALAR;
   s.tiles_y = (s.nyl + 2 + lbm::kTileH - 1) / lbm::kTileH;
-  s.grid = h->ntx * s.tiles_y;
+  s.grid = s.ntx_sweep * s.tiles_y;
   // Lattices that fit in L2 twice over (the reference's shipped inputs) run their whole time loop as ONE cooperative
   // launch with a grid barrier per step (sweep_persistent_kernel).  LBM_B200_PERSISTENT=0 disables, =1 forces
   // (any size, for tests).
@@ -282,8 +290,8 @@ int alloc_slab(lbm_handle *h, Slab &s) {
   CUDA_TRY(cudaMalloc((void **)&s.row_partials, (size_t)lbm::kWindowSteps * h->tiles_y * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s.tot_u, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
   CUDA_TRY(cudaMemset(s.tot_u, 0, (size_t)std::max(h->max_iters, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&s.ticket, 4 * sizeof(unsigned)));
-  CUDA_TRY(cudaMemset(s.ticket, 0, 4 * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc((void **)&s.ticket, 16 * sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(s.ticket, 0, 16 * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc((void **)&s.step, 2 * sizeof(int)));
   CUDA_TRY(cudaMemset(s.step, 0, 2 * sizeof(int)));
   CUDA_TRY(cudaMalloc((void **)&s.free_dev, sizeof(unsigned long long)));
@@ -332,16 +340,19 @@ int check_problem(int nx, int ny, int max_iters, int slabs) {
   return LBM_OK;
 }
 
+// `ring` row slabs (px == 1), or px x ring blocks with ghost columns (xghost)
 void set_geometry(lbm_handle *h, int nx, int ny, int max_iters, float density, float accel, float omega,
-                  int ring) {
+                  int ring, int px = 1, bool xghost = false) {
   h->nx = nx; h->ny = ny; h->max_iters = max_iters;
   h->density = density; h->accel = accel; h->omega = omega;
-  h->ntx = (nx + lbm::kTileW - 1) / lbm::kTileW;
+  h->px = px; h->py = ring; h->xghost = xghost;
+  const int widest = (nx + px - 1) / px;
+  h->ntx = (widest + lbm::kTileW - 1) / lbm::kTileW + (xghost ? 1 : 0);  // + the halo tile column; same on every block
   h->rows_alloc = (ny + ring - 1) / ring + 2;  // the tallest slab + two ghost rows; same on every slab
   h->tiles_y = (h->rows_alloc + lbm::kTileH - 1) / lbm::kTileH;
   h->lattice_floats = (size_t)h->tiles_y * h->ntx * lbm::kTileFloats;
   h->lattice_bytes = h->lattice_floats * sizeof(float);
-  h->multi = ring > 1;
+  h->multi = ring > 1 || xghost;
 }
 
 lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
@@ -354,8 +365,9 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   a.mask = s.mask;
   a.lattice_floats = h->lattice_floats;
   a.ntx = h->ntx;
+  a.ntx_sweep = s.ntx_sweep;
   a.tiles_y = s.tiles_y;
-  a.nx = h->nx;
+  a.nx = s.nxl;
   a.nyl = s.nyl;
   a.south_ghost_row = s.south_ghost_row;
   const int arow = h->ny - 2;  // main/LastChance.cpp:198 (never matches when ny < 2, like the reference)
@@ -374,6 +386,12 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   a.flag_to_south = s.flag_to_south;
   a.flag_to_north = s.flag_to_north;
   a.error = s.step + 1;
+  for (int i = 0; i < 6; ++i) {
+    a.side_dst[i] = s.side_buf[i][c ^ 1];
+    a.flag_to_side[i] = s.flag_to_side[i];
+  }
+  a.flag_from_side = s.flags + 2;
+  a.sdiag_ghost_row = s.south_ghost_row;
   return a;
 }
 
@@ -397,8 +415,8 @@ cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, bool pdl, const 
 // Finish the sums of the timesteps whose CTA partials wait in the slab's window: tot_u[window_first ...].
 int flush_reductions(lbm_handle *h, Slab &s) {
   if (s.window_count == 0) return LBM_OK;
-  lbm::reduce_rows_kernel<<<dim3((unsigned)s.tiles_y, (unsigned)s.window_count), 256, 0, s.stream>>>(s.partials, s.row_partials, h->ntx,
-                                                                                                 s.tiles_y);
+  lbm::reduce_rows_kernel<<<dim3((unsigned)s.tiles_y, (unsigned)s.window_count), 256, 0, s.stream>>>(s.partials, s.row_partials,
+                                                                                                 s.ntx_sweep, s.tiles_y);
   lbm::reduce_total_kernel<<<(unsigned)s.window_count, 256, 0, s.stream>>>(s.row_partials, s.tot_u, s.tiles_y, s.window_first,
                                                                            h->graph_capture ? s.step : nullptr);
   h->launches += 2;
@@ -422,15 +440,15 @@ int launch_sweep(lbm_handle *h, Slab &s, int t, bool overlap) {
   ++s.window_count;
   const bool pdl = overlap && pdl_enabled;
   cudaError_t e;
-  if (s.kernel == KERNEL_VEC4)
-    e = h->multi ? launch_pdl(lbm::sweep_kernel<lbm::SWEEP_VEC4, true>, s.grid, s.stream, pdl, a)
-                 : launch_pdl(lbm::sweep_kernel<lbm::SWEEP_VEC4, false>, s.grid, s.stream, pdl, a);
-  else if (s.kernel == KERNEL_HYBRID)
-    e = h->multi ? launch_pdl(lbm::sweep_kernel<lbm::SWEEP_HYBRID, true>, s.grid, s.stream, pdl, a)
-                 : launch_pdl(lbm::sweep_kernel<lbm::SWEEP_HYBRID, false>, s.grid, s.stream, pdl, a);
-  else
-    e = h->multi ? launch_pdl(lbm::sweep_kernel<lbm::SWEEP_SCALAR, true>, s.grid, s.stream, pdl, a)
-                 : launch_pdl(lbm::sweep_kernel<lbm::SWEEP_SCALAR, false>, s.grid, s.stream, pdl, a);
+  const int multi = h->xghost ? 2 : (h->multi ? 1 : 0);
+#define LBM_SWEEP(MODE)                                                                              \
+  (multi == 2   ? launch_pdl(lbm::sweep_kernel<MODE, 2>, s.grid, s.stream, pdl, a)                    \
+   : multi == 1 ? launch_pdl(lbm::sweep_kernel<MODE, 1>, s.grid, s.stream, pdl, a)                    \
+                : launch_pdl(lbm::sweep_kernel<MODE, 0>, s.grid, s.stream, pdl, a))
+  if (s.kernel == KERNEL_VEC4) e = LBM_SWEEP(lbm::SWEEP_VEC4);
+  else if (s.kernel == KERNEL_HYBRID) e = LBM_SWEEP(lbm::SWEEP_HYBRID);
+  else e = LBM_SWEEP(lbm::SWEEP_SCALAR);
+#undef LBM_SWEEP
   if (e != cudaSuccess) return fail(LBM_E_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
   ++h->launches;
   KERNEL_CHECK(s.stream, "sweep");
@@ -506,15 +524,22 @@ int launch_cluster(lbm_handle *h, Slab &s, int iters) {
 constexpr size_t kHalfStage = kStageBytes / 2;
 
 // host -> staging half (copy_stream) -> `consume(stage_half, first_row, rows)` launches a kernel on s.stream
+// (host rows are `host_pitch` bytes apart: the rows of a 2-D block are pieces of the caller's full-width rows)
+cudaError_t copy_rows(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows, cudaMemcpyKind kind,
+                      cudaStream_t stream) {
+  if (dpitch == row_bytes && spitch == row_bytes) return cudaMemcpyAsync(dst, src, (size_t)rows * row_bytes, kind, stream);
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, (size_t)rows, kind, stream);
+}
+
 template <typename Consume>
-int stage_in(Slab &s, const char *host, size_t row_bytes, int total_rows, int &chunk, Consume consume) {
+int stage_in(Slab &s, const char *host, size_t host_pitch, size_t row_bytes, int total_rows, int &chunk, Consume consume) {
   if (row_bytes > kHalfStage) return fail(LBM_E_ARG, "a single row of %zu bytes does not fit the staging buffer", row_bytes);
   const int rows_per_chunk = (int)std::max<size_t>(1, kHalfStage / row_bytes);
   for (int r = 0; r < total_rows; r += rows_per_chunk, ++chunk) {
     const int rows = std::min(rows_per_chunk, total_rows - r), b = chunk & 1;
     char *half = reinterpret_cast<char *>(s.stage) + (size_t)b * kHalfStage;
     if (chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.drained[b], 0));  // its previous user has read it
-    CUDA_TRY(cudaMemcpyAsync(half, host + (size_t)r * row_bytes, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, s.copy_stream));
+    CUDA_TRY(copy_rows(half, row_bytes, host + (size_t)r * host_pitch, host_pitch, row_bytes, rows, cudaMemcpyHostToDevice, s.copy_stream));
     CUDA_TRY(cudaEventRecord(s.filled[b], s.copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(s.stream, s.filled[b], 0));
     int rc = consume(half, r, rows);
@@ -525,7 +550,7 @@ int stage_in(Slab &s, const char *host, size_t row_bytes, int total_rows, int &c
 }
 // `produce(stage_half, first_row, rows)` launches a kernel on s.stream -> staging half -> host (copy_stream)
 template <typename Produce>
-int stage_out(Slab &s, char *host, size_t row_bytes, int total_rows, int &chunk, Produce produce) {
+int stage_out(Slab &s, char *host, size_t host_pitch, size_t row_bytes, int total_rows, int &chunk, Produce produce) {
   if (row_bytes > kHalfStage) return fail(LBM_E_ARG, "a single row of %zu bytes does not fit the staging buffer", row_bytes);
   const int rows_per_chunk = (int)std::max<size_t>(1, kHalfStage / row_bytes);
   for (int r = 0; r < total_rows; r += rows_per_chunk, ++chunk) {
@@ -536,7 +561,7 @@ int stage_out(Slab &s, char *host, size_t row_bytes, int total_rows, int &chunk,
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s.filled[b], s.stream));
     CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.filled[b], 0));
-    CUDA_TRY(cudaMemcpyAsync(host + (size_t)r * row_bytes, half, (size_t)rows * row_bytes, cudaMemcpyDeviceToHost, s.copy_stream));
+    CUDA_TRY(copy_rows(host + (size_t)r * host_pitch, host_pitch, half, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, s.copy_stream));
     CUDA_TRY(cudaEventRecord(s.drained[b], s.copy_stream));
   }
   return LBM_OK;
@@ -585,7 +610,7 @@ int reset_counters(lbm_handle *h) {
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     CUDA_TRY(cudaMemsetAsync(s.flags, 0, kFlagBytes, s.stream));
-    CUDA_TRY(cudaMemsetAsync(s.ticket, 0, 4 * sizeof(unsigned), s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.ticket, 0, 16 * sizeof(unsigned), s.stream));
     s.window_first = 0;
     s.window_count = 0;
     CUDA_TRY(cudaMemsetAsync(s.step, 0, 2 * sizeof(int), s.stream));
@@ -666,6 +691,8 @@ int lbm_create_on_devices(lbm_handle **out, int nx, int ny, int max_iters, float
     s.device = devices[i];
     s.row0 = (int)((long long)i * ny / num_slabs);
     s.nyl = (int)((long long)(i + 1) * ny / num_slabs) - s.row0;
+    s.nxl = nx;
+    s.ntx_sweep = h->ntx;
     // slabs sharing a device share one stream, so their kernels run back to back (no co-scheduling
     // assumption between kernels that wait on each other)
     for (int j = 0; j < i; ++j)
@@ -699,6 +726,107 @@ int lbm_create(lbm_handle **out, int nx, int ny, int max_iters, float density, f
   return lbm_create_on_devices(out, nx, ny, max_iters, density, accel, omega, num_gpus, dev.data());
 }
 
+}  // extern "C"
+namespace {
+// wire a px x py block partition inside one process: block (bx, by) sits at index by * px + bx; both directions are
+// periodic, so with px == 1 (or py == 1) a block is its own east / west (north / south) neighbour
+int wire_local_grid(lbm_handle *h) {
+  const int px = h->px, py = h->py;
+  auto at = [&](int bx, int by) -> Slab & { return h->slabs[(size_t)((by + py) % py) * px + (bx + px) % px]; };
+  for (int by = 0; by < py; ++by)
+    for (int bx = 0; bx < px; ++bx) {
+      Slab &s = at(bx, by);
+      Slab &so = at(bx, by - 1), &no = at(bx, by + 1);
+      for (int b = 0; b < 2; ++b) {
+        s.south_buf[b] = so.buf[b];
+        s.north_buf[b] = no.buf[b];
+      }
+      s.flag_to_south = so.flags + 1;  // its "from north"
+      s.flag_to_north = no.flags + 0;  // its "from south"
+      s.south_ghost_row = so.nyl + 1;
+      // side i of this block -> (neighbour, the side of the neighbour this block is on)
+      const struct { int dx, dy, back; } sides[6] = {{-1, 0, lbm::SIDE_E},  {1, 0, lbm::SIDE_W},   {-1, -1, lbm::SIDE_NE},
+                                                     {1, -1, lbm::SIDE_NW}, {-1, 1, lbm::SIDE_SE}, {1, 1, lbm::SIDE_SW}};
+      for (int i = 0; i < 6; ++i) {
+        Slab &nb = at(bx + sides[i].dx, by + sides[i].dy);
+        for (int b = 0; b < 2; ++b) s.side_buf[i][b] = nb.buf[b];
+        s.flag_to_side[i] = nb.flags + 2 + sides[i].back;
+      }
+    }
+  // peer access between every pair of distinct devices that are neighbours (8-neighbourhood)
+  for (int by = 0; by < py; ++by)
+    for (int bx = 0; bx < px; ++bx)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int me = at(bx, by).device, d = at(bx + dx, by + dy).device;
+          if (d == me) continue;
+          int can = 0;
+          CUDA_TRY(cudaDeviceCanAccessPeer(&can, me, d));
+          if (!can) return fail(LBM_E_PEER, "GPU %d cannot access GPU %d as a peer", me, d);
+          CUDA_TRY(cudaSetDevice(me));
+          cudaError_t e = cudaDeviceEnablePeerAccess(d, 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+          else if (e != cudaSuccess)
+            return fail(LBM_E_PEER, "cudaDeviceEnablePeerAccess(%d -> %d): %s", me, d, cudaGetErrorString(e));
+        }
+  h->connected = true;
+  return LBM_OK;
+}
+}  // namespace
+extern "C" {
+
+int lbm_create_grid(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel, float omega, int px,
+                    int py, const int *devices) {
+  if (!out) return fail(LBM_E_ARG, "null argument");
+  *out = nullptr;
+  if (px < 1 || py < 1 || px > 64 || py > 64) return fail(LBM_E_ARG, "the block grid must be 1..64 x 1..64 (got %d x %d)", px, py);
+  int rc = check_problem(nx, ny, max_iters, py);
+  if (rc) return rc;
+  if (nx < px) return fail(LBM_E_ARG, "cannot cut %d columns into %d blocks", nx, px);
+  int ndev = 0;
+  rc = lbm_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev < 1) return fail(LBM_E_CUDA, "no CUDA device present; this library has no CPU path");
+  const int n = px * py;
+  std::vector<int> dev(n);
+  for (int i = 0; i < n; ++i) {
+    dev[i] = devices ? devices[i] : i;
+    if (dev[i] < 0 || dev[i] >= ndev)
+      return fail(LBM_E_ARG, "block %d asks for GPU %d but only %d are visible", i, dev[i], ndev);
+  }
+  lbm_handle *h = new (std::nothrow) lbm_handle();
+  if (!h) return fail(LBM_E_NOMEM, "out of host memory");
+  set_geometry(h, nx, ny, max_iters, density, accel, omega, py, px, true);
+  h->slabs.resize(n);
+  for (int by = 0; by < py; ++by)
+    for (int bx = 0; bx < px; ++bx) {
+      const int i = by * px + bx;
+      Slab &s = h->slabs[i];
+      s.device = dev[i];
+      s.row0 = (int)((long long)by * ny / py);
+      s.nyl = (int)((long long)(by + 1) * ny / py) - s.row0;
+      s.col0 = (int)((long long)bx * nx / px);
+      s.nxl = (int)((long long)(bx + 1) * nx / px) - s.col0;
+      s.ntx_sweep = (s.nxl + lbm::kTileW - 1) / lbm::kTileW;
+      for (int j = 0; j < i; ++j)
+        if (h->slabs[j].device == s.device) { s.stream = h->slabs[j].stream; break; }
+      if (!s.stream) {
+        cudaError_t e = cudaSetDevice(s.device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+          lbm_destroy(h);
+          return fail(LBM_E_CUDA, "stream creation on GPU %d: %s", s.device, cudaGetErrorString(e));
+        }
+        s.owns_stream = true;
+      }
+    }
+  rc = create_common(out, h);
+  if (rc) return rc;
+  rc = wire_local_grid(h);
+  if (rc) { lbm_destroy(h); *out = nullptr; return rc; }
+  return LBM_OK;
+}
+
 int lbm_create_rank(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel,
                     float omega, int rank, int world, int device) {
   if (!out) return fail(LBM_E_ARG, "null argument");
@@ -721,6 +849,8 @@ int lbm_create_rank(lbm_handle **out, int nx, int ny, int max_iters, float densi
   s.device = device;
   s.row0 = (int)((long long)rank * ny / world);
   s.nyl = (int)((long long)(rank + 1) * ny / world) - s.row0;
+  s.nxl = nx;
+  s.ntx_sweep = h->ntx;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
@@ -833,32 +963,33 @@ void lbm_destroy(lbm_handle *h) {
 }  // extern "C"
 namespace {
 
-// Global rows [g0, g0 + n) of the problem -> the slabs that own them.  `cells` / `obstacles` point at row g0.
+// Global rows [g0, g0 + n) of the problem -> the slabs / blocks that own them.  `cells` / `obstacles` point at row g0 of
+// full-width rows (nx cells apart), from which every block takes its own columns.
 int upload_rows(lbm_handle *h, int g0, int n, const float *cells, const uint8_t *obstacles) {
   const int nx = h->nx;
   for (Slab &s : h->slabs) {
     const int lo = std::max(g0, s.row0), hi = std::min(g0 + n, s.row0 + s.nyl);
     if (lo >= hi) continue;
     CUDA_TRY(cudaSetDevice(s.device));
-    const float *c = cells + (size_t)(lo - g0) * nx * lbm::kSpeeds;
-    const uint8_t *o = obstacles + (size_t)(lo - g0) * nx;
-    const int first_storage_row = 1 + (lo - s.row0);
+    const float *c = cells + ((size_t)(lo - g0) * nx + s.col0) * lbm::kSpeeds;
+    const uint8_t *o = obstacles + (size_t)(lo - g0) * nx + s.col0;
+    const int first_storage_row = 1 + (lo - s.row0), nxl = s.nxl;
     // cells: AoS rows -> tiles; obstacles: bytes -> bits.  Chunks of whole rows, PCIe copy of one half of the
     // staging buffer overlapped with the transposition of the other
-    int rc = stage_in(s, reinterpret_cast<const char *>(c), (size_t)nx * lbm::kSpeeds * sizeof(float), hi - lo, s.stage_chunk,
-                      [&](char *stage, int r, int rows) {
-                        lbm::aos_to_tiles_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
-                            reinterpret_cast<const float *>(stage), s.buf[0], h->ntx, nx, rows, first_storage_row + r);
+    int rc = stage_in(s, reinterpret_cast<const char *>(c), (size_t)nx * lbm::kSpeeds * sizeof(float),
+                      (size_t)nxl * lbm::kSpeeds * sizeof(float), hi - lo, s.stage_chunk, [&](char *stage, int r, int rows) {
+                        lbm::aos_to_tiles_kernel<<<rows * s.ntx_sweep, lbm::kTileW, 0, s.stream>>>(
+                            reinterpret_cast<const float *>(stage), s.buf[0], h->ntx, nxl, rows, first_storage_row + r, s.ntx_sweep);
                         ++h->launches;
                         KERNEL_CHECK(s.stream, "aos_to_tiles");
                         return (int)LBM_OK;
                       });
     if (rc) return rc;
-    const int words = (nx + 31) / 32;
-    rc = stage_in(s, reinterpret_cast<const char *>(o), (size_t)nx, hi - lo, s.stage_chunk, [&](char *stage, int r, int rows) {
+    const int words = (nxl + 31) / 32;
+    rc = stage_in(s, reinterpret_cast<const char *>(o), (size_t)nx, (size_t)nxl, hi - lo, s.stage_chunk, [&](char *stage, int r, int rows) {
       const long long threads = (long long)rows * words * 32;
       lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
-          reinterpret_cast<const uint8_t *>(stage), s.mask, h->ntx, nx, rows, first_storage_row + r, s.free_dev);
+          reinterpret_cast<const uint8_t *>(stage), s.mask, h->ntx, nxl, rows, first_storage_row + r, s.free_dev);
       ++h->launches;
       KERNEL_CHECK(s.stream, "pack_mask");
       return (int)LBM_OK;
@@ -877,19 +1008,20 @@ int drain_all(lbm_handle *h) {
   }
   return LBM_OK;
 }
-// Global rows [g0, g0 + n) of the current state -> host AoS / obstacle bytes (either may be null)
+// Global rows [g0, g0 + n) of the current state -> host AoS / obstacle bytes (either may be null), full-width rows
 int download_rows(lbm_handle *h, int g0, int n, float *cells, uint8_t *obstacles) {
   const int nx = h->nx;
   for (Slab &s : h->slabs) {
     const int lo = std::max(g0, s.row0), hi = std::min(g0 + n, s.row0 + s.nyl);
     if (lo >= hi) continue;
     CUDA_TRY(cudaSetDevice(s.device));
-    const int first_storage_row = 1 + (lo - s.row0);
+    const int first_storage_row = 1 + (lo - s.row0), nxl = s.nxl;
     if (cells) {
-      int rc = stage_out(s, reinterpret_cast<char *>(cells + (size_t)(lo - g0) * nx * lbm::kSpeeds),
-                         (size_t)nx * lbm::kSpeeds * sizeof(float), hi - lo, s.stage_chunk, [&](char *stage, int r, int rows) {
-                           lbm::tiles_to_aos_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
-                               s.buf[h->cur], reinterpret_cast<float *>(stage), h->ntx, nx, rows, first_storage_row + r);
+      int rc = stage_out(s, reinterpret_cast<char *>(cells + ((size_t)(lo - g0) * nx + s.col0) * lbm::kSpeeds),
+                         (size_t)nx * lbm::kSpeeds * sizeof(float), (size_t)nxl * lbm::kSpeeds * sizeof(float), hi - lo, s.stage_chunk,
+                         [&](char *stage, int r, int rows) {
+                           lbm::tiles_to_aos_kernel<<<rows * s.ntx_sweep, lbm::kTileW, 0, s.stream>>>(
+                               s.buf[h->cur], reinterpret_cast<float *>(stage), h->ntx, nxl, rows, first_storage_row + r, s.ntx_sweep);
                            ++h->launches;
                            KERNEL_CHECK(s.stream, "tiles_to_aos");
                            return (int)LBM_OK;
@@ -897,11 +1029,11 @@ int download_rows(lbm_handle *h, int g0, int n, float *cells, uint8_t *obstacles
       if (rc) return rc;
     }
     if (obstacles) {
-      int rc = stage_out(s, reinterpret_cast<char *>(obstacles + (size_t)(lo - g0) * nx), (size_t)nx, hi - lo, s.stage_chunk,
-                         [&](char *stage, int r, int rows) {
-                           const long long cellsn = (long long)rows * nx;
+      int rc = stage_out(s, reinterpret_cast<char *>(obstacles + (size_t)(lo - g0) * nx + s.col0), (size_t)nx, (size_t)nxl, hi - lo,
+                         s.stage_chunk, [&](char *stage, int r, int rows) {
+                           const long long cellsn = (long long)rows * nxl;
                            lbm::unpack_mask_kernel<<<(unsigned)((cellsn + 255) / 256), 256, 0, s.stream>>>(
-                               s.mask, reinterpret_cast<uint8_t *>(stage), h->ntx, nx, rows, first_storage_row + r);
+                               s.mask, reinterpret_cast<uint8_t *>(stage), h->ntx, nxl, rows, first_storage_row + r);
                            ++h->launches;
                            KERNEL_CHECK(s.stream, "unpack_mask");
                            return (int)LBM_OK;
@@ -941,10 +1073,10 @@ int lbm_init_synthetic(lbm_handle *h, uint64_t seed, float solid_prob) {
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     lbm::fill_lattice_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[0], h->lattice_floats, w0, w1, w2);
-    const int words = (h->nx + 31) / 32;
+    const int words = (s.nxl + 31) / 32;
     const long long threads = (long long)s.nyl * words * 32;
     lbm::synthetic_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
-        s.mask, h->ntx, h->nx, h->ny, s.row0, s.nyl, seed, threshold24, s.free_dev);
+        s.mask, h->ntx, h->nx, h->ny, s.row0, s.nyl, seed, threshold24, s.free_dev, s.col0, s.nxl);
     h->launches += 2;
     KERNEL_CHECK(s.stream, "fill_lattice/synthetic_mask");
   }
@@ -1061,7 +1193,7 @@ bool graphs_wanted(const lbm_handle *h, int iters) {
   if (env == 0 || g_debug_sync || iters < kGraphSteps) return false;
   if (env == 1) return true;
   for (const Slab &s : h->slabs)
-    if ((long long)s.nyl * h->nx > kGraphMaxCells) return false;
+    if ((long long)s.nyl * s.nxl > kGraphMaxCells) return false;
   return true;
 }
 
@@ -1095,7 +1227,7 @@ int lbm_run(lbm_handle *h, int iters) {
     for (Slab &s : h->slabs) {
       if (arow < s.row0 || arow >= s.row0 + s.nyl) continue;
       CUDA_TRY(cudaSetDevice(s.device));
-      lbm::accelerate_flow_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(s.buf[h->cur], h->ntx, h->nx, arow - s.row0 + 1,
+      lbm::accelerate_flow_kernel<<<(s.nxl + 255) / 256, 256, 0, s.stream>>>(s.buf[h->cur], h->ntx, s.nxl, arow - s.row0 + 1,
                                                                              s.mask, w1, w2);
       ++h->launches;
       KERNEL_CHECK(s.stream, "accelerate_flow");
@@ -1122,12 +1254,25 @@ int lbm_run(lbm_handle *h, int iters) {
     // publishes the epoch the next timestep waits for
     for (Slab &s : h->slabs) {
       CUDA_TRY(cudaSetDevice(s.device));
-      lbm::init_halo_kernel<<<(h->nx + 255) / 256, 256, 0, s.stream>>>(s.buf[h->cur], s.north_buf[h->cur], s.south_buf[h->cur],
-                                                                       h->ntx, h->nx, s.nyl, s.south_ghost_row);
+      lbm::init_halo_kernel<<<(s.nxl + 255) / 256, 256, 0, s.stream>>>(s.buf[h->cur], s.north_buf[h->cur], s.south_buf[h->cur],
+                                                                       h->ntx, s.nxl, s.nyl, s.south_ghost_row);
       ++h->launches;
+      lbm::SidePointers side{};
+      if (h->xghost) {  // 2-D blocks: ghost columns and corners as well
+        for (int i = 0; i < 6; ++i) {
+          side.dst[i] = s.side_buf[i][h->cur];
+          side.flag[i] = s.flag_to_side[i];
+        }
+        lbm::init_halo_sides_kernel<<<(s.nyl + 255) / 256, 256, 0, s.stream>>>(s.buf[h->cur], side, h->ntx, s.nxl, s.nyl, s.south_ghost_row);
+        ++h->launches;
+      }
       if (h->multi) {
         lbm::publish_epoch_kernel<<<1, 1, 0, s.stream>>>(s.flag_to_south, s.flag_to_north, h->steps_done + 1);
         ++h->launches;
+        if (h->xghost) {
+          lbm::publish_epoch_sides_kernel<<<1, 1, 0, s.stream>>>(side, h->steps_done + 1);
+          ++h->launches;
+        }
       }
       KERNEL_CHECK(s.stream, "init_halo/publish_epoch");
     }
@@ -1241,10 +1386,11 @@ int lbm_download_fields(lbm_handle *h, float *fields) {
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
-    int rc = stage_out(s, reinterpret_cast<char *>(fields + first * nx * 4), (size_t)nx * 4 * sizeof(float), s.nyl, s.stage_chunk,
-                       [&](char *stage, int r, int rows) {
-                         lbm::final_state_kernel<<<rows * h->ntx, lbm::kTileW, 0, s.stream>>>(
-                             s.buf[h->cur], s.mask, reinterpret_cast<float4 *>(stage), h->ntx, nx, rows, 1 + r, h->density);
+    const int nxl = s.nxl;
+    int rc = stage_out(s, reinterpret_cast<char *>(fields + (first * nx + s.col0) * 4), (size_t)nx * 4 * sizeof(float),
+                       (size_t)nxl * 4 * sizeof(float), s.nyl, s.stage_chunk, [&](char *stage, int r, int rows) {
+                         lbm::final_state_kernel<<<rows * s.ntx_sweep, lbm::kTileW, 0, s.stream>>>(
+                             s.buf[h->cur], s.mask, reinterpret_cast<float4 *>(stage), h->ntx, nxl, rows, 1 + r, h->density, s.ntx_sweep);
                          ++h->launches;
                          KERNEL_CHECK(s.stream, "final_state");
                          return (int)LBM_OK;
@@ -1435,6 +1581,26 @@ int lbm_slab_info(lbm_handle *h, int slab, int *device, int *row_begin, int *row
   if (row_begin) *row_begin = s.row0;
   if (row_count) *row_count = s.nyl;
   if (free_cells) *free_cells = h->uploaded ? s.free_cells : -1;
+  return LBM_OK;
+}
+
+int lbm_block_info(lbm_handle *h, int block, int *device, int *row_begin, int *row_count, int *col_begin, int *col_count,
+                   long long *free_cells) {
+  if (!h) return fail(LBM_E_ARG, "null argument");
+  if (block < 0 || block >= (int)h->slabs.size()) return fail(LBM_E_ARG, "block %d of %zu", block, h->slabs.size());
+  const Slab &s = h->slabs[block];
+  if (device) *device = s.device;
+  if (row_begin) *row_begin = s.row0;
+  if (row_count) *row_count = s.nyl;
+  if (col_begin) *col_begin = s.col0;
+  if (col_count) *col_count = s.nxl;
+  if (free_cells) *free_cells = h->uploaded ? s.free_cells : -1;
+  return LBM_OK;
+}
+int lbm_partition(lbm_handle *h, int *px, int *py) {
+  if (!h) return fail(LBM_E_ARG, "null argument");
+  if (px) *px = h->px;
+  if (py) *py = h->py;
   return LBM_OK;
 }
 
