@@ -5,6 +5,7 @@
 // There is no CPU path in this file: every compute entry point needs a CUDA device.
 #include "../../include/lbm_b200.h"
 #include "lbm_kernels.cuh"
+#include "lbm_partition.hpp"
 
 #include <algorithm>
 #include <cctype>
@@ -689,8 +690,7 @@ int lbm_create_on_devices(lbm_handle **out, int nx, int ny, int max_iters, float
   for (int i = 0; i < num_slabs; ++i) {
     Slab &s = h->slabs[i];
     s.device = devices[i];
-    s.row0 = (int)((long long)i * ny / num_slabs);
-    s.nyl = (int)((long long)(i + 1) * ny / num_slabs) - s.row0;
+    lbm::partition::range_of(ny, num_slabs, i, s.row0, s.nyl);
     s.nxl = nx;
     s.ntx_sweep = h->ntx;
     // slabs sharing a device share one stream, so their kernels run back to back (no co-scheduling
@@ -803,10 +803,8 @@ int lbm_create_grid(lbm_handle **out, int nx, int ny, int max_iters, float densi
       const int i = by * px + bx;
       Slab &s = h->slabs[i];
       s.device = dev[i];
-      s.row0 = (int)((long long)by * ny / py);
-      s.nyl = (int)((long long)(by + 1) * ny / py) - s.row0;
-      s.col0 = (int)((long long)bx * nx / px);
-      s.nxl = (int)((long long)(bx + 1) * nx / px) - s.col0;
+      lbm::partition::range_of(ny, py, by, s.row0, s.nyl);
+      lbm::partition::range_of(nx, px, bx, s.col0, s.nxl);
       s.ntx_sweep = (s.nxl + lbm::kTileW - 1) / lbm::kTileW;
       for (int j = 0; j < i; ++j)
         if (h->slabs[j].device == s.device) { s.stream = h->slabs[j].stream; break; }
@@ -847,8 +845,7 @@ int lbm_create_rank(lbm_handle **out, int nx, int ny, int max_iters, float densi
   h->slabs.resize(1);
   Slab &s = h->slabs[0];
   s.device = device;
-  s.row0 = (int)((long long)rank * ny / world);
-  s.nyl = (int)((long long)(rank + 1) * ny / world) - s.row0;
+  lbm::partition::range_of(ny, world, rank, s.row0, s.nyl);
   s.nxl = nx;
   s.ntx_sweep = h->ntx;
   cudaError_t e = cudaSetDevice(device);

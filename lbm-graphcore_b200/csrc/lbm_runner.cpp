@@ -25,6 +25,7 @@
 
 #include "../../include/lbm_b200.h"
 #include "lbm_host.hpp"
+#include "lbm_partition.hpp"
 
 namespace {
 
@@ -230,6 +231,26 @@ int main(int argc, char *argv[]) {
     std::cerr << "No CUDA device available (" << lbm_last_error() << "); this solver has no CPU path" << std::endl;
     return EXIT_FAILURE;
   }
+  // --grid PXxPY | auto: a 2-D block partition instead of row slabs ("auto": the reference's rule for 2/4/8/16 devices)
+  int grid_px = 0, grid_py = 0;
+  if (!opt.grid.empty()) {
+    if (opt.grid == "auto") {
+      lbm::partition::grid_for_gpus(static_cast<int>(params->nx), static_cast<int>(params->ny), opt.num_gpus, grid_px, grid_py);
+    } else {
+      char *end = nullptr;
+      grid_px = static_cast<int>(std::strtol(opt.grid.c_str(), &end, 10));
+      if (end && (*end == 'x' || *end == 'X')) grid_py = static_cast<int>(std::strtol(end + 1, nullptr, 10));
+    }
+    if (grid_px < 1 || grid_py < 1) {
+      std::cerr << "--grid wants PXxPY or auto (got " << opt.grid << ")" << std::endl;
+      return EXIT_FAILURE;
+    }
+    if (opt.num_gpus != 1 && opt.num_gpus != grid_px * grid_py) {
+      std::cerr << "--grid " << grid_px << "x" << grid_py << " needs -n " << grid_px * grid_py << " (got " << opt.num_gpus << ")" << std::endl;
+      return EXIT_FAILURE;
+    }
+    opt.num_gpus = grid_px * grid_py;
+  }
   std::cout << "Running on " << opt.num_gpus << " of " << ndev << " visible GPU(s)" << std::endl;
 
   // --exe FILE: the reference's "compiled graph" (main/LbmRunner.cpp:20,75-84).  When the file exists the solver is
@@ -273,8 +294,12 @@ int main(int argc, char *argv[]) {
     params->maxIters = static_cast<size_t>(max_iters);
   } else {
     timedStep("Creating solver and allocating device lattices", [&]() {
-      rc = lbm_create(&engine, static_cast<int>(params->nx), static_cast<int>(params->ny),
-                      static_cast<int>(params->maxIters), params->density, params->accel, params->omega, opt.num_gpus);
+      if (grid_px > 0)  // 2-D blocks with ghost columns (the reference's partitionForIpus layout)
+        rc = lbm_create_grid(&engine, static_cast<int>(params->nx), static_cast<int>(params->ny), static_cast<int>(params->maxIters),
+                             params->density, params->accel, params->omega, grid_px, grid_py, nullptr);
+      else
+        rc = lbm_create(&engine, static_cast<int>(params->nx), static_cast<int>(params->ny),
+                        static_cast<int>(params->maxIters), params->density, params->accel, params->omega, opt.num_gpus);
     });
     if (rc != LBM_OK) return die("lbm_create");
     timedStep("Running copy to device step", [&]() {
@@ -330,6 +355,29 @@ int main(int argc, char *argv[]) {
   }
 
   const double cell_updates = static_cast<double>(params->nx) * static_cast<double>(params->ny) * static_cast<double>(iters);
+  if (opt.stats) {
+    // partition quality, the numbers of the reference's tile_mapping_stats restated for GPUs (lbm_partition.hpp), plus what
+    // only the device knows: the non-obstacle cells of every block
+    int ppx = 1, ppy = 1, nblocks = 0;
+    lbm_partition(engine, &ppx, &ppy);
+    lbm_slab_count(engine, &nblocks);
+    const auto st = lbm::partition::stats(static_cast<int>(params->nx), static_cast<int>(params->ny), ppx, ppy, grid_px > 0);
+    std::cout << lbm::partition::csv_header() << std::endl
+              << lbm::partition::csv_row(static_cast<int>(params->nx), static_cast<int>(params->ny), st) << std::endl;
+    long long most_free = 0, all_free = 0;
+    for (int i = 0; i < nblocks; ++i) {
+      int dev = 0, r0 = 0, nr = 0, c0 = 0, nc = 0;
+      long long free_cells = 0;
+      lbm_block_info(engine, i, &dev, &r0, &nr, &c0, &nc, &free_cells);
+      std::cout << "Block " << i << ": GPU " << dev << ", rows [" << r0 << ", " << r0 + nr << "), cols [" << c0 << ", " << c0 + nc << "), "
+                << free_cells << " free cells" << std::endl;
+      most_free = std::max(most_free, free_cells);
+      all_free += free_cells;
+    }
+    std::cout << "Free-cell load balance: " << std::fixed << std::setprecision(2)
+              << (most_free ? 100.0 * static_cast<double>(all_free) / nblocks / static_cast<double>(most_free) : 100.0) << " %" << std::endl;
+    std::cout.unsetf(std::ios::floatfield);
+  }
   if (opt.debug) {
     const double mlups = cell_updates / (device_ms * 1e-3) / 1e6;
     std::cout << "Kernel variant:      \t" << lbm_kernel_variant(engine) << std::endl;
