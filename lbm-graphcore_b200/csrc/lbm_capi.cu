@@ -213,8 +213,8 @@ int configure_launch(lbm_handle *h, Slab &s) {
     }
   }
   // The smallest inputs (nx = 128 or 256, a few dozen K cells) keep both lattices in the distributed shared memory of
-  // thread-block clusters (sweep_cluster_kernel): CTAs of 256, 512 or 1024 cells -- the smallest whose CTAs can all be
-  // co-resident -- one cell per thread (two at 1024), the largest cluster size <= 16 that divides the CTA count and fits.  LBM_B200_CLUSTER=0 disables; LBM_B200_CLUSTER_CELLS /
+  // thread-block clusters (sweep_cluster_kernel): CTAs of 512 cells (1024 if that many CTAs cannot be co-resident; 256 on
+  // request) -- one cell per thread (two at 1024), the largest cluster size <= 16 that divides the CTA count and fits.  LBM_B200_CLUSTER=0 disables; LBM_B200_CLUSTER_CELLS /
   // _CPT / _SIZE pin the shape (tuning runs).
   s.cluster_ctas = 0;
   const int want_cluster = getenv("LBM_B200_CLUSTER") ? atoi(getenv("LBM_B200_CLUSTER")) : 1;
@@ -226,7 +226,7 @@ int configure_launch(lbm_handle *h, Slab &s) {
     const int env_cs = getenv("LBM_B200_CLUSTER_SIZE") ? atoi(getenv("LBM_B200_CLUSTER_SIZE")) : 0;
     // smallest CTAs first: the update is issue-bound per SM, so the more SMs share a lattice the shorter a step
     // (profiles/r02b_small_grids_cluster_v3.txt: 128^2 1.31 / 0.86 us per step with 1024 / 512 cells per CTA)
-    for (int cells : {256, 512, 1024}) {
+    for (int cells : {512, 1024, 256}) {  // (256-cell CTAs measured no faster than 512: twice the SMs for the same step time)
       if (s.cluster_ctas > 0) break;
       if (env_cells && env_cells != cells) continue;
       const int rows = cells / h->nx, cpt = env_cpt ? env_cpt : (cells == 1024 ? 2 : 1);

@@ -76,7 +76,30 @@ def test_block_grid_argument_errors(lbm):
     p = lbm.Params(64, 64, 1, 10, 0.1, 0.005, 1.85)
     with pytest.raises(lbm.LbmError):
         lbm.Solver(p, grid=(0, 1))
-    with pytest.raises(lbm.LbmError, match="columns"):
+    with pytest.raises(lbm.LbmError, match="1..64"):
         lbm.Solver(p, grid=(65, 1), devices=[0] * 65)
+    with pytest.raises(lbm.LbmError, match="columns"):
+        lbm.Solver(lbm.Params(8, 64, 1, 10, 0.1, 0.005, 1.85), grid=(16, 1), devices=[0] * 16)
     with pytest.raises(lbm.LbmError, match="GPU"):
         lbm.Solver(p, grid=(1, 2), devices=[0, 99])
+
+
+def test_lbm_runner_grid_and_stats(lbm, tmp_path):
+    """lbm_runner --grid PXxPY (all blocks on GPU 0 here is not expressible through the CLI, so 1x1 with ghost columns) and
+    --stats: same output files as the row-slab run, plus the partition report."""
+    from conftest import obstacles_path, params_path
+    import subprocess
+    outs = []
+    for extra in ([], ["--grid", "1x1", "--stats"]):
+        d = tmp_path / ("grid" if extra else "plain")
+        d.mkdir()
+        r = subprocess.run([lbm.RUNNER_PATH, "--params", params_path("128x256"), "--obstacles", obstacles_path("128x256"), "--outdir", str(d),
+                            "--iters", "2000", "--reruns", "0", *extra], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        if extra:
+            assert "numGpus,width,height,px,py" in r.stdout and "Block 0: GPU 0, rows [0, 256), cols [0, 128)" in r.stdout
+            assert "Free-cell load balance: 100.00 %" in r.stdout
+        outs.append(d)
+    assert (outs[0] / "final_state.dat").read_bytes() == (outs[1] / "final_state.dat").read_bytes()
+    a, b = (np.loadtxt(o / "av_vels.dat", usecols=[1]).astype(np.float32) for o in outs)
+    assert ulp_distance(a, b).max() <= 1

@@ -84,3 +84,23 @@ def test_lbm_runner_on_two_gpus_writes_the_same_files(lbm, tmp_path):
     assert (outs[0] / "final_state.dat").read_bytes() == (outs[1] / "final_state.dat").read_bytes()
     a, b = (np.loadtxt(o / "av_vels.dat", usecols=[1]).astype(np.float32) for o in outs)
     assert ulp_distance(a, b).max() <= 1
+
+
+@pytest.mark.parametrize("nx,ny,px,py", [(512, 64, 2, 1), (300, 50, 1, 2), (1024, 96, 2, 2), (640, 100, 2, 2), (1024, 128, 4, 2),
+                                         (1024, 128, 2, 4), (777, 90, 4, 2)])
+def test_block_partition_across_gpus_bit_exact(oracle, lbm, nx, ny, px, py):
+    """lbm_create_grid with one block per GPU: ghost columns, ghost rows and corners travel over NVLink (2 x 2 on four GPUs,
+    2 x 4 and 4 x 2 on eight; the reference's partitionForIpus layouts, main/include/StructuredGridUtils.hpp:501-527)."""
+    _need_gpus(lbm, px * py)
+    iters = 40
+    p, cells, obst = problem(lbm, nx, ny, iters, seed=nx + ny + px * py)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    with lbm.Solver(p, grid=(px, py)) as s:
+        assert sorted(b["device"] for b in s.blocks) == list(range(px * py))
+        s.upload(cells, obst)
+        s.run(17)
+        s.run(iters - 17)
+        got_cells, got_av = s.download()
+    assert np.array_equal(got_cells.view(np.uint32), want_cells.view(np.uint32))
+    assert ulp_distance(got_av, want_av).max() <= 1
