@@ -64,6 +64,10 @@ def parse_args():
     ap.add_argument("--ny", type=int, default=0, help="override the grid height (development only)")
     ap.add_argument("--local-slabs", type=int, default=1,
                     help="development only: cut the grid into this many row slabs that all live on GPU 0")
+    ap.add_argument("--in-process", type=int, default=0, metavar="N",
+                    help="comparison runs: ONE process drives N GPUs (lbm_create / lbm_create_grid) instead of one rank per GPU")
+    ap.add_argument("--grid", default="", metavar="PXxPY",
+                    help="with --in-process: cut the grid into PX x PY blocks with ghost columns instead of N row slabs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -476,7 +480,17 @@ def main():
     K, W = args.steps, args.warmup
     p = lbm.Params(nx, ny, W + K, REYNOLDS_DIM, DENSITY, ACCEL, OMEGA)
 
-    if world == 1:
+    inproc = args.in_process if world == 1 else 0
+    if inproc:  # comparison of partitions: one process, N GPUs, row slabs or PX x PY blocks
+        if args.grid:
+            gx, gy = (int(v) for v in args.grid.lower().split("x"))
+            if gx * gy != inproc:
+                raise SystemExit(f"--grid {args.grid} needs --in-process {gx * gy}")
+            solver = lbm.Solver(p, grid=(gx, gy))
+        else:
+            solver = lbm.Solver(p, num_gpus=inproc)
+        args.no_e2e = args.no_parity = args.no_weak = args.no_shipped = args.no_cpu_baseline = True
+    elif world == 1:
         solver = lbm.Solver(p, devices=[0] * args.local_slabs) if args.local_slabs > 1 else lbm.Solver(p, num_gpus=1)
     else:
         solver = lbm.Solver(p, rank=rank, world=world, device=local_rank)
@@ -586,33 +600,36 @@ def main():
 
     # ---- roofline ------------------------------------------------------------------------------
     launch_ms = ms / K  # one sweep launch per step per GPU
-    achieved = (cells / world) * BYTES_PER_CELL / (launch_ms * 1e-3) / 1e9
+    gpus_used = inproc or world
+    achieved = (cells / gpus_used) * BYTES_PER_CELL / (launch_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             for entry in tj.get("entries", [tj]):
-                if entry.get("cells_per_launch") == cells // world and bool(entry.get("multi", False)) == (world > 1 or args.local_slabs > 1):
+                if entry.get("cells_per_launch") == cells // gpus_used and bool(entry.get("multi", False)) == (gpus_used > 1 or args.local_slabs > 1):
                     traffic = entry.get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
-    multi = world > 1 or args.local_slabs > 1
+    multi = gpus_used > 1 or args.local_slabs > 1 or bool(args.grid)
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel": f"lbm::sweep_kernel<SWEEP_{variant.upper()},{'true' if multi else 'false'}>",
-                "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": cells // world,
+                "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": cells // gpus_used,
                 "avg_launch_ms": round(launch_ms, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
                 "context": "best plain copy measured on this pool with tools/probes/stream_probe.cu: 6920 GB/s "
                            "(profiles/r01c_stream_probe_4.txt); ncu reports 85 % DRAM throughput for this kernel"}
 
     line = {
-        "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": gpus_used, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(name, nx, ny),
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches * world), "clocks": clocks,
-        "detail": {"partition": f"{world} row slab(s), one per GPU" if args.local_slabs <= 1 else f"{args.local_slabs} row slabs on one GPU",
+        "detail": {"partition": (f"{args.grid} blocks with ghost columns, one per GPU, one process" if (inproc and args.grid) else
+                                 f"{inproc} row slabs, one per GPU, one process" if inproc else
+                                 f"{world} row slab(s), one per GPU" if args.local_slabs <= 1 else f"{args.local_slabs} row slabs on one GPU"),
                    "kernel_variant": variant, "av_vels_last": av_last, "wall_ms_per_step": round(wall * 1e3 / K, 4)},
     }
     if parity is not None:
