@@ -162,6 +162,25 @@ int lbm_load(lbm_handle **out, const char *path, int num_gpus);
 /* the problem a handle was created (or loaded) for; any pointer may be NULL */
 int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density, float *accel, float *omega);
 
+/* One whole job from host buffers -- what main/LbmRunner.cpp:98-108 does with run(0), run(1), run(2) -- as ONE call that
+ * overlaps the three: the grid is solved in horizontal bands (a band plus a margin of >= iters rows either side is all
+ * that `iters` timesteps of the band depend on), so that uploads, sweeps and downloads of different bands run concurrently
+ * and both directions of PCIe are busy at once.  Like the Engine, the pipeline is prepared once for a fixed problem
+ * (lbm_pipeline_create allocates its band solvers) and can then solve any number of inputs of that shape:
+ *   cells_in / obstacles / cells_out / av_vels as for lbm_upload / lbm_download; cells_out must NOT alias cells_in (the
+ *   margins of a band are read again after its neighbours have been written); pinned buffers (lbm_host_alloc) for full speed.
+ * Same results as upload + run + download on one GPU: lattice bit-identical, av_vels from per-band sums added in band
+ * order.  Grids too small (or step counts too large) for bands to pay run the three calls on one internal handle.
+ * lbm_solve_host = create + solve + destroy. */
+typedef struct lbm_pipeline lbm_pipeline;
+int lbm_pipeline_create(lbm_pipeline **out, int nx, int ny, int iters, float density, float accel, float omega, int device);
+int lbm_pipeline_solve(lbm_pipeline *p, const float *cells_in, const uint8_t *obstacles, float *cells_out, float *av_vels);
+/* how the job is cut (1 band = not banded) and the wall time of the last solve; any pointer may be NULL */
+int lbm_pipeline_info(lbm_pipeline *p, int *bands, int *band_rows, int *margin_rows, double *last_ms);
+void lbm_pipeline_destroy(lbm_pipeline *p);
+int lbm_solve_host(int nx, int ny, int iters, float density, float accel, float omega, int device, const float *cells_in,
+                   const uint8_t *obstacles, float *cells_out, float *av_vels, double *elapsed_ms);
+
 /* Self-test of the kernels' IEEE division / square-root helpers against CUDA's __fdiv_rn / __fsqrt_rn on
  * GPU `device`: exhaustive for x/9, x/36 and sqrt(x), `pairs` random operand pairs for a/b.
  * counts[7] = {x/9 mismatches, sqrt mismatches, a/b mismatches, x/36 mismatches, #x/9, #sqrt, #a/b}. */

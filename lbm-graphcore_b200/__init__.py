@@ -35,7 +35,8 @@ ABI_SYMBOLS = (
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_host_alloc_near", "lbm_bind_thread_near", "lbm_create_rank", "lbm_ipc_blob_bytes",
-    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_problem", "lbm_create_grid", "lbm_partition", "lbm_block_info", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
+    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_problem", "lbm_create_grid", "lbm_partition", "lbm_block_info", "lbm_solve_host", "lbm_pipeline_create", "lbm_pipeline_solve",
+    "lbm_pipeline_info", "lbm_pipeline_destroy", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
 )
 
 
@@ -94,6 +95,13 @@ def _load() -> ctypes.CDLL:
     lib.lbm_create_grid.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_int, P(c_int)]
     lib.lbm_partition.argtypes = [c_void_p, P(c_int), P(c_int)]
     lib.lbm_block_info.argtypes = [c_void_p, c_int, P(c_int), P(c_int), P(c_int), P(c_int), P(c_int), P(ctypes.c_longlong)]
+    lib.lbm_solve_host.argtypes = [c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   P(ctypes.c_double)]
+    lib.lbm_pipeline_create.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int]
+    lib.lbm_pipeline_solve.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.lbm_pipeline_info.argtypes = [c_void_p, P(c_int), P(c_int), P(c_int), P(ctypes.c_double)]
+    lib.lbm_pipeline_destroy.argtypes = [c_void_p]
+    lib.lbm_pipeline_destroy.restype = None
     lib.lbm_save.argtypes = [c_void_p, ctypes.c_char_p]
     lib.lbm_load.argtypes = [P(c_void_p), ctypes.c_char_p, c_int]
     lib.lbm_problem.argtypes = [c_void_p, P(c_int), P(c_int), P(c_int), P(c_float), P(c_float), P(c_float)]
@@ -120,6 +128,65 @@ def selftest_math(device: int = 0, pairs: int = 1 << 32) -> dict:
 def host_alloc(nbytes: int, device: int | None = None) -> int:
     """Pinned host memory (address, or 0/None on failure); near GPU `device`'s NUMA node when given. Free with lib.lbm_host_free."""
     return lib.lbm_host_alloc(nbytes) if device is None else lib.lbm_host_alloc_near(nbytes, device)
+
+
+class Pipeline:
+    """lbm_pipeline: whole jobs (upload, `iters` timesteps, download) of one problem shape, band-pipelined over PCIe."""
+
+    def __init__(self, params: Params, iters: int | None = None, device: int = 0):
+        p = params
+        self.params, self.iters = p, (p.max_iters if iters is None else iters)
+        self._p = ctypes.c_void_p()
+        _check(lib.lbm_pipeline_create(ctypes.byref(self._p), p.nx, p.ny, self.iters, p.density, p.accel, p.omega, device))
+
+    def solve_raw(self, cells_in_ptr: int, obstacles_ptr: int, cells_out_ptr: int, av_vels_ptr: int | None) -> None:
+        _check(lib.lbm_pipeline_solve(self._p, cells_in_ptr, obstacles_ptr, cells_out_ptr, av_vels_ptr))
+
+    def solve(self, cells: np.ndarray, obstacles: np.ndarray):
+        cells = np.ascontiguousarray(cells, dtype=np.float32)
+        obstacles = np.ascontiguousarray(obstacles).astype(np.uint8, copy=False)
+        out = np.empty_like(cells)
+        av = np.zeros(max(self.iters, 1), dtype=np.float32)
+        self.solve_raw(cells.ctypes.data, obstacles.ctypes.data, out.ctypes.data, av.ctypes.data)
+        return out, av[: self.iters]
+
+    @property
+    def info(self) -> dict:
+        b, r, m, ms = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        _check(lib.lbm_pipeline_info(self._p, ctypes.byref(b), ctypes.byref(r), ctypes.byref(m), ctypes.byref(ms)))
+        return {"bands": b.value, "band_rows": r.value, "margin_rows": m.value, "last_ms": ms.value}
+
+    def close(self) -> None:
+        if self._p:
+            lib.lbm_pipeline_destroy(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def solve_host(params: Params, cells: np.ndarray, obstacles: np.ndarray, iters: int | None = None, device: int = 0):
+    """lbm_solve_host: the whole job (upload, `iters` timesteps, download) as one pipelined call.  Returns
+    (cells float32[ny, nx, 9], av_vels float32[iters], elapsed_ms)."""
+    p = params
+    iters = p.max_iters if iters is None else iters
+    cells = np.ascontiguousarray(cells, dtype=np.float32)
+    obstacles = np.ascontiguousarray(obstacles).astype(np.uint8, copy=False)
+    out = np.empty_like(cells)
+    av = np.zeros(max(iters, 1), dtype=np.float32)
+    ms = ctypes.c_double()
+    _check(lib.lbm_solve_host(p.nx, p.ny, iters, p.density, p.accel, p.omega, device, cells.ctypes.data, obstacles.ctypes.data,
+                              out.ctypes.data, av.ctypes.data, ctypes.byref(ms)))
+    return out, av[:iters], ms.value
 
 
 def device_count() -> int:

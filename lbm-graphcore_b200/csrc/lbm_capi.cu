@@ -13,8 +13,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <mutex>
 #include <new>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <sched.h>
@@ -112,6 +116,8 @@ struct Slab {
   // launch configuration
   int kernel = 0;  // KERNEL_SCALAR / KERNEL_VEC4 / KERNEL_HYBRID
   int tiles_y = 1; // tile rows this slab sweeps = ceil((nyl + 2) / 8)
+  int tot_ty_lo = 0, tot_ty_hi = -1;    // tile rows whose cells count towards tot_u (-1: all); free cells: storage rows ...
+  int count_lo = 0, count_hi = 1 << 30; // ... [count_lo, count_hi).  Only the bands of lbm_solve_host restrict these.
   int grid = 1;    // one CTA per tile
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long free_cells = 0;
@@ -145,6 +151,7 @@ struct lbm_handle {
   int rank = 0, world = 1;
   bool connected = false;
   std::vector<void *> ipc_opened;
+  int accel_row_global = 0;  // the driven row: ny - 2 (main/LastChance.cpp:198); a band of lbm_solve_host holds it elsewhere or not at all
   int cur = 0;  // which lattice holds the current state
   int steps_done = 0;
   bool uploaded = false;
@@ -153,6 +160,7 @@ struct lbm_handle {
   double last_ms = 0.0;
   long long launches = 0;
   // time loop as a CUDA graph (one per distinct stream and per lattice parity), built on first use and replayed
+  bool no_graphs = false;          // band solvers of lbm_solve_host: their driven row changes from band to band
   bool graph_capture = false;      // launches are being captured: kernels take the step number from device memory
   int graph_state[2] = {0, 0};     // per parity: 0 not built, 1 ready, -1 unavailable
   std::vector<StreamGraph> graphs;
@@ -354,6 +362,7 @@ void set_geometry(lbm_handle *h, int nx, int ny, int max_iters, float density, f
   h->lattice_floats = (size_t)h->tiles_y * h->ntx * lbm::kTileFloats;
   h->lattice_bytes = h->lattice_floats * sizeof(float);
   h->multi = ring > 1 || xghost;
+  h->accel_row_global = ny - 2;
 }
 
 lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
@@ -371,7 +380,7 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   a.nx = s.nxl;
   a.nyl = s.nyl;
   a.south_ghost_row = s.south_ghost_row;
-  const int arow = h->ny - 2;  // main/LastChance.cpp:198 (never matches when ny < 2, like the reference)
+  const int arow = h->accel_row_global;  // main/LastChance.cpp:198 (never matches when ny < 2, like the reference)
   a.accel_row = (arow >= s.row0 && arow < s.row0 + s.nyl) ? (arow - s.row0 + 1) : -1;
   a.omega = h->omega;
   a.one_minus_omega = 1 - h->omega;                 // main/LastChance.cpp:387
@@ -419,7 +428,8 @@ int flush_reductions(lbm_handle *h, Slab &s) {
   lbm::reduce_rows_kernel<<<dim3((unsigned)s.tiles_y, (unsigned)s.window_count), 256, 0, s.stream>>>(s.partials, s.row_partials,
                                                                                                  s.ntx_sweep, s.tiles_y);
   lbm::reduce_total_kernel<<<(unsigned)s.window_count, 256, 0, s.stream>>>(s.row_partials, s.tot_u, s.tiles_y, s.window_first,
-                                                                           h->graph_capture ? s.step : nullptr);
+                                                                           h->graph_capture ? s.step : nullptr, s.tot_ty_lo,
+                                                                           s.tot_ty_hi < 0 ? s.tiles_y : s.tot_ty_hi);
   h->launches += 2;
   KERNEL_CHECK(s.stream, "reduce_rows/reduce_total");
   s.window_first += s.window_count;
@@ -491,7 +501,7 @@ int launch_cluster(lbm_handle *h, Slab &s, int iters) {
   a.error = s.step + 1;
   a.ntx = h->ntx;
   a.ny = h->ny;
-  a.accel_row = h->ny - 2;
+  a.accel_row = h->accel_row_global;
   a.omega = h->omega;
   a.one_minus_omega = 1 - h->omega;
   a.w1 = h->density * h->accel / 9.f;
@@ -986,7 +996,7 @@ int upload_rows(lbm_handle *h, int g0, int n, const float *cells, const uint8_t 
     rc = stage_in(s, reinterpret_cast<const char *>(o), (size_t)nx, (size_t)nxl, hi - lo, s.stage_chunk, [&](char *stage, int r, int rows) {
       const long long threads = (long long)rows * words * 32;
       lbm::pack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s.stream>>>(
-          reinterpret_cast<const uint8_t *>(stage), s.mask, h->ntx, nxl, rows, first_storage_row + r, s.free_dev);
+          reinterpret_cast<const uint8_t *>(stage), s.mask, h->ntx, nxl, rows, first_storage_row + r, s.free_dev, s.count_lo, s.count_hi);
       ++h->launches;
       KERNEL_CHECK(s.stream, "pack_mask");
       return (int)LBM_OK;
@@ -1187,7 +1197,7 @@ int build_graphs(lbm_handle *h, int parity) {
 
 bool graphs_wanted(const lbm_handle *h, int iters) {
   const int env = getenv("LBM_B200_GRAPH") ? atoi(getenv("LBM_B200_GRAPH")) : -1;  // 0 off, 1 force, default auto
-  if (env == 0 || g_debug_sync || iters < kGraphSteps) return false;
+  if (env == 0 || g_debug_sync || iters < kGraphSteps || h->no_graphs) return false;
   if (env == 1) return true;
   for (const Slab &s : h->slabs)
     if ((long long)s.nyl * s.nxl > kGraphMaxCells) return false;
@@ -1220,7 +1230,7 @@ int lbm_run(lbm_handle *h, int iters) {
   if (h->first_run_pending) {
     // accelerate_flow once before step 0 (main/LbmAoS.cpp:352; main/LastChance.cpp:158-183) ...
     const float w1 = h->density * h->accel / 9.f, w2 = h->density * h->accel / 36.f;
-    const int arow = h->ny - 2;
+    const int arow = h->accel_row_global;
     for (Slab &s : h->slabs) {
       if (arow < s.row0 || arow >= s.row0 + s.nyl) continue;
       CUDA_TRY(cudaSetDevice(s.device));
@@ -1524,6 +1534,217 @@ int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density,
   if (accel) *accel = h->accel;
   if (omega) *omega = h->omega;
   return LBM_OK;
+}
+
+// ---- one whole job from host buffers, pipelined -------------------------------------------------------
+// lbm_upload -> lbm_run -> lbm_download is strictly sequential: PCIe carries 36 B per cell up, then nothing, then 36 B per
+// cell down (2 x 9.66 GB at 16384^2, 0.36 s at 55 GB/s each way for 56 ms of arithmetic).  But information travels one row per
+// timestep, so after K steps a band of rows depends only on itself plus K rows either side of the INITIAL state: the grid
+// can be solved band by band -- upload a band with a margin of M >= K rows on both sides, run K steps on it (the band's own
+// periodic wrap feeds garbage into the margins, which never reaches the band), download the band -- and the bands' uploads,
+// sweeps and downloads overlap, which keeps both directions of the link busy at once.  Worker threads each drive their
+// own band solver (an ordinary single-slab handle, created once per pipeline); one band uploads at a time and one downloads
+// at a time, so each direction runs at its full rate.  The lattice is bit-identical to the sequential job; tot_u is summed
+// per band over the band's own tile rows only (M + 1 is a multiple of the tile height) and the bands are added in band order.
+}  // extern "C"
+
+struct lbm_pipeline {
+  int nx = 0, ny = 0, iters = 0, device = 0;
+  float density = 0, accel = 0, omega = 0;
+  bool banded = false;
+  int margin = 0, band_rows = 0, nbands = 1, workers = 1;
+  std::vector<lbm_handle *> full, last;  // per worker: a solver for full bands, and (if ny % band_rows) one for the shorter last band
+  lbm_handle *whole = nullptr;           // not banded: the sequential job on one handle
+  std::mutex up, down;                   // one band uploads / downloads at a time
+  double last_ms = 0.0;
+};
+
+namespace {
+constexpr int kSolveWorkers = 3;
+constexpr long long kSolveBandCells = 16ll << 20;  // cells per band (without margins): ~0.6 GB of lattice each way
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct BandJob {
+  const float *cells_in;
+  const uint8_t *obstacles;
+  float *cells_out;
+  std::vector<std::vector<double>> tot;  // [band][step]
+  std::vector<long long> free_cells;     // [band]
+  double t_begin = 0;
+};
+
+int solve_band(lbm_pipeline *p, lbm_handle *h, BandJob &job, int b) {
+  static const bool trace = getenv("LBM_B200_SOLVE_TRACE") != nullptr;
+  const int nx = p->nx, ny = p->ny, M = p->margin;
+  const int r0 = b * p->band_rows, rows = std::min(p->band_rows, ny - r0), total = rows + 2 * M;
+  Slab &s = h->slabs[0];
+  // the band's rows -M .. rows + M - 1 are global rows r0 - M ... (periodic); the driven row may or may not be among them
+  const int first = ((r0 - M) % ny + ny) % ny;
+  const int arow = ((ny - 2 - first) % ny + ny) % ny;
+  h->accel_row_global = (ny >= 2 && arow < total) ? arow : -1;
+  s.tot_ty_lo = (M + 1) / lbm::kTileH;
+  s.tot_ty_hi = s.tot_ty_lo + rows / lbm::kTileH;
+  s.count_lo = M + 1;
+  s.count_hi = M + 1 + rows;
+  double t_a, t_b, t_c, t_d;
+  int rc;
+  {
+    std::lock_guard<std::mutex> lock(p->up);
+    t_a = now_ms();
+    rc = reset_counters(h);
+    for (int done = 0; done < total && rc == LBM_OK;) {  // contiguous pieces of the periodic row range
+      const int g = (first + done) % ny, n = std::min(total - done, ny - g);
+      rc = upload_rows(h, done, n, job.cells_in + (size_t)g * nx * lbm::kSpeeds, job.obstacles + (size_t)g * nx);
+      done += n;
+    }
+    if (rc == LBM_OK) rc = drain_all(h);
+    if (rc == LBM_OK) rc = finish_upload(h);
+    t_b = now_ms();
+  }
+  if (rc == LBM_OK) rc = lbm_run(h, p->iters);
+  if (rc) return rc;
+  t_c = now_ms();
+  job.free_cells[b] = s.free_cells;
+  {
+    std::lock_guard<std::mutex> lock(p->down);
+    t_d = now_ms();
+    rc = download_rows(h, M, rows, job.cells_out + (size_t)r0 * nx * lbm::kSpeeds, nullptr);
+    if (rc == LBM_OK) rc = drain_all(h);
+  }
+  if (rc) return rc;
+  job.tot[b].assign((size_t)p->iters, 0.0);
+  if (p->iters) CUDA_TRY(cudaMemcpy(job.tot[b].data(), s.tot_u, (size_t)p->iters * sizeof(double), cudaMemcpyDeviceToHost));
+  if (trace)
+    fprintf(stderr, "band %2d: upload %.1f..%.1f  run ..%.1f (device %.1f)  download %.1f..%.1f ms\n", b, t_a - job.t_begin, t_b - job.t_begin,
+            t_c - job.t_begin, h->last_ms, t_d - job.t_begin, now_ms() - job.t_begin);
+  return LBM_OK;
+}
+}  // namespace
+extern "C" {
+
+void lbm_pipeline_destroy(lbm_pipeline *p) {
+  if (!p) return;
+  for (lbm_handle *h : p->full) lbm_destroy(h);
+  for (lbm_handle *h : p->last) lbm_destroy(h);
+  lbm_destroy(p->whole);
+  delete p;
+}
+
+int lbm_pipeline_create(lbm_pipeline **out, int nx, int ny, int iters, float density, float accel, float omega, int device) {
+  if (!out) return fail(LBM_E_ARG, "null argument");
+  *out = nullptr;
+  int rc = check_problem(nx, ny, iters, 1);
+  if (rc) return rc;
+  lbm_pipeline *p = new (std::nothrow) lbm_pipeline();
+  if (!p) return fail(LBM_E_NOMEM, "out of host memory");
+  p->nx = nx; p->ny = ny; p->iters = iters; p->device = device;
+  p->density = density; p->accel = accel; p->omega = omega;
+  // the margin: >= iters rows, and M + 1 a multiple of the tile height so that a band is whole tile rows of its solver
+  p->margin = ((std::max(iters, 1) + 1 + lbm::kTileH - 1) / lbm::kTileH) * lbm::kTileH - 1;
+  p->band_rows = (int)std::max<long long>(lbm::kTileH, kSolveBandCells / nx / lbm::kTileH * lbm::kTileH);
+  if (const char *e = getenv("LBM_B200_BAND_ROWS")) p->band_rows = std::max(lbm::kTileH, atoi(e) / lbm::kTileH * lbm::kTileH);  // tests
+  // bands pay when the margins are a small part of a band and there are enough bands to overlap
+  p->banded = ny % lbm::kTileH == 0 && p->band_rows >= 8 * p->margin && ny >= 4 * p->band_rows && !getenv("LBM_B200_NO_BANDS");
+  if (!p->banded) {
+    rc = lbm_create_on_devices(&p->whole, nx, ny, iters, density, accel, omega, 1, &device);
+    if (rc) { lbm_pipeline_destroy(p); return rc; }
+    *out = p;
+    return LBM_OK;
+  }
+  p->nbands = (ny + p->band_rows - 1) / p->band_rows;
+  p->workers = std::min(kSolveWorkers, p->nbands);
+  if (const char *e = getenv("LBM_B200_SOLVE_WORKERS")) p->workers = std::max(1, std::min(atoi(e), p->nbands));
+  const int last_rows = ny - (p->nbands - 1) * p->band_rows;
+  auto band_solver = [&](int rows, lbm_handle **slot) {
+    int r = lbm_create_on_devices(slot, nx, rows + 2 * p->margin, iters, density, accel, omega, 1, &device);
+    if (r == LBM_OK) {  // bands take the plain per-step kernel (a cached graph would bake in one band's driven row)
+      (*slot)->slabs[0].persistent_grid = 0;
+      (*slot)->slabs[0].cluster_ctas = 0;
+      (*slot)->no_graphs = true;
+    }
+    return r;
+  };
+  p->full.assign(p->workers, nullptr);
+  p->last.assign(p->workers, nullptr);
+  for (int w = 0; w < p->workers && rc == LBM_OK; ++w) {
+    rc = band_solver(p->band_rows, &p->full[w]);
+    // the last band goes to worker (nbands - 1) % workers
+    if (rc == LBM_OK && last_rows != p->band_rows && w == (p->nbands - 1) % p->workers) rc = band_solver(last_rows, &p->last[w]);
+  }
+  if (rc) { lbm_pipeline_destroy(p); return rc; }
+  *out = p;
+  return LBM_OK;
+}
+
+int lbm_pipeline_solve(lbm_pipeline *p, const float *cells_in, const uint8_t *obstacles, float *cells_out, float *av_vels) {
+  if (!p || !cells_in || !obstacles || !cells_out) return fail(LBM_E_ARG, "null argument");
+  if (cells_in == cells_out) return fail(LBM_E_ARG, "cells_out must not alias cells_in");
+  const double t_begin = now_ms();
+  int rc = LBM_OK;
+  if (!p->banded) {
+    rc = lbm_upload(p->whole, cells_in, obstacles);
+    if (rc == LBM_OK) rc = lbm_run(p->whole, p->iters);
+    if (rc == LBM_OK) rc = lbm_download(p->whole, cells_out, av_vels);
+    p->last_ms = now_ms() - t_begin;
+    return rc;
+  }
+  try {
+    BandJob job{};
+    job.cells_in = cells_in; job.obstacles = obstacles; job.cells_out = cells_out;
+    job.tot.resize(p->nbands);
+    job.free_cells.assign(p->nbands, 0);
+    job.t_begin = t_begin;
+    std::vector<int> codes(p->workers, LBM_OK);
+    std::vector<std::string> messages(p->workers);
+    std::vector<std::thread> threads;
+    for (int w = 0; w < p->workers; ++w)
+      threads.emplace_back([&, w]() {
+        for (int b = w; b < p->nbands && codes[w] == LBM_OK; b += p->workers) {
+          const int rows = std::min(p->band_rows, p->ny - b * p->band_rows);
+          lbm_handle *h = rows == p->band_rows ? p->full[w] : p->last[w];
+          const int r = solve_band(p, h, job, b);
+          if (r != LBM_OK) { codes[w] = r; messages[w] = g_last_error; }
+        }
+      });
+    for (std::thread &t : threads) t.join();
+    for (int w = 0; w < p->workers; ++w)
+      if (codes[w] != LBM_OK) return fail(codes[w], "band solver: %s", messages[w].c_str());
+    if (av_vels) {
+      long long free_cells = 0;
+      for (long long f : job.free_cells) free_cells += f;
+      for (int t = 0; t < p->iters; ++t) {
+        double tot = 0.0;
+        for (int b = 0; b < p->nbands; ++b) tot += job.tot[b][t];  // band order
+        av_vels[t] = (float)tot / (float)free_cells;                // main/LastChance.cpp:266
+      }
+    }
+  } catch (const std::exception &e) {  // thread or host-memory exhaustion: nothing may throw across the ABI
+    return fail(LBM_E_NOMEM, "lbm_pipeline_solve: %s", e.what());
+  }
+  p->last_ms = now_ms() - t_begin;
+  return LBM_OK;
+}
+
+int lbm_pipeline_info(lbm_pipeline *p, int *bands, int *band_rows, int *margin_rows, double *last_ms) {
+  if (!p) return fail(LBM_E_ARG, "null argument");
+  if (bands) *bands = p->banded ? p->nbands : 1;
+  if (band_rows) *band_rows = p->banded ? p->band_rows : p->ny;
+  if (margin_rows) *margin_rows = p->banded ? p->margin : 0;
+  if (last_ms) *last_ms = p->last_ms;
+  return LBM_OK;
+}
+
+int lbm_solve_host(int nx, int ny, int iters, float density, float accel, float omega, int device, const float *cells_in,
+                   const uint8_t *obstacles, float *cells_out, float *av_vels, double *elapsed_ms) {
+  const double t_begin = now_ms();
+  lbm_pipeline *p = nullptr;
+  int rc = lbm_pipeline_create(&p, nx, ny, iters, density, accel, omega, device);
+  if (rc) return rc;
+  rc = lbm_pipeline_solve(p, cells_in, obstacles, cells_out, av_vels);
+  lbm_pipeline_destroy(p);
+  if (elapsed_ms) *elapsed_ms = now_ms() - t_begin;
+  return rc;
 }
 
 // ---- introspection -------------------------------------------------------------------------------
