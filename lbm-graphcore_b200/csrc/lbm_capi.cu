@@ -62,7 +62,6 @@ constexpr size_t kStageBytes = 64u << 20;  // AoS staging chunk for upload/downl
 constexpr int kClusterChunkSteps = 8192;  // timesteps per launch of the cluster-resident kernel
 constexpr int kPersistentMaxCtas = 1024;  // upper bound on the persistent kernel's grid
 constexpr size_t kPersistentPartials = 2 * (size_t)kPersistentMaxCtas * lbm::kTileH;
-constexpr size_t kPersistentMaxBytes = 96u << 20;  // both lattices must stay in the 126 MB L2 for the persistent kernel to pay
 
 struct Slab {
   int device = 0;
@@ -201,12 +200,13 @@ int configure_launch(lbm_handle *h, Slab &s) {
     if (!strcmp(e, "scalar")) s.kernel = KERNEL_SCALAR;
   s.tiles_y = (s.nyl + 2 + lbm::kTileH - 1) / lbm::kTileH;
   s.grid = s.ntx_sweep * s.tiles_y;
-  // Lattices that fit in L2 twice over (the reference's shipped inputs) run their whole time loop as ONE cooperative
-  // launch with a grid barrier per step (sweep_persistent_kernel).  LBM_B200_PERSISTENT=0 disables, =1 forces
-  // (any size, for tests).
+  // sweep_persistent_kernel runs the whole time loop as ONE cooperative launch with a grid barrier per step.  It was the
+  // default for lattices that fit in L2 until the per-step loop was replayed from a CUDA graph, which is as fast or faster at
+  // every size (profiles/r02j_mid_grids.txt: 768^2 7.2 vs 8.6 us per step, 1024^2 12.8 vs 13.3, 2048^2 48.6 vs 51.6) and needs
+  // no co-residency.  LBM_B200_PERSISTENT=1 still selects it (tests, comparisons); =0 also switches the cluster kernel off.
   s.persistent_grid = 0;
   const int want = getenv("LBM_B200_PERSISTENT") ? atoi(getenv("LBM_B200_PERSISTENT")) : -1;
-  if (!h->multi && want != 0 && (want == 1 || 2 * h->lattice_bytes <= kPersistentMaxBytes)) {
+  if (!h->multi && want == 1) {
     CUDA_TRY(cudaSetDevice(s.device));
     int sms = 0, coop = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));

@@ -51,13 +51,17 @@ def test_shipped_inputs_bit_exact_short(oracle, lbm, case):
 
 @pytest.mark.parametrize("nx,ny", [(100, 37), (3, 2), (1, 1), (31, 5), (257, 3), (130, 64), (129, 6), (255, 7), (127, 14),
                                    (385, 15), (2, 8), (1, 23), (1000, 30), (640 + 77, 9)])
-def test_ragged_widths_hybrid_and_scalar_kernels(oracle, lbm, nx, ny):
+@pytest.mark.parametrize("persistent", [None, "1"])
+def test_ragged_widths_hybrid_and_scalar_kernels(oracle, lbm, monkeypatch, nx, ny, persistent):
     """Widths that are not a multiple of the tile (nx % 128 != 0): float4 path on the full tiles + scalar path on the
     last tile column ("hybrid"), scalar only below 128; including the reference KAT shape 3x2 and 1x1; last
-    tile columns with 1, 2 and 127 cells; slab heights that put the north ghost row in a tile of its own."""
+    tile columns with 1, 2 and 127 cells; slab heights that put the north ghost row in a tile of its own.  Through the
+    per-step kernels (default; 40 steps = two graph replays + 8 plain launches) and the persistent cooperative kernel."""
+    if persistent:
+        monkeypatch.setenv("LBM_B200_PERSISTENT", persistent)
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 40, seed=nx * 1000 + ny)
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == ("hybrid-persistent" if nx > 128 else "scalar-persistent")
+        assert s.kernel_variant == ("hybrid" if nx > 128 else "scalar") + ("-persistent" if persistent else "")
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 40)
 
 
@@ -76,7 +80,7 @@ def test_scalar_kernel_on_vectorisable_sizes(oracle, lbm, nx, ny, monkeypatch):
     monkeypatch.setenv("LBM_B200_KERNEL", "scalar")
     p, op, cells, obst = _random_problem(oracle, lbm, nx, ny, 30, seed=nx * 7 + ny, solid_frac=0.1)
     with lbm.Solver(p) as s:
-        assert s.kernel_variant == "scalar-persistent"
+        assert s.kernel_variant == "scalar"
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30)
     _assert_matches_oracle(oracle, lbm, p, op, cells, obst, 30, devices=[0, 0])
 
@@ -175,10 +179,11 @@ def test_division_and_sqrt_helpers_match_ieee_library(lbm):
 
 
 @pytest.mark.parametrize("density,accel,omega", [(0.1, 0.0, 1.85), (1.0, 0.01, 0.6), (0.05, 0.002, 1.99), (0.3, 0.02, 1.0)])
-@pytest.mark.parametrize("nx,ny,env", [(256, 24, None), (200, 17, None), (256, 24, "0")])
+@pytest.mark.parametrize("nx,ny,env", [(256, 24, None), (200, 17, "1"), (256, 24, "1"), (256, 64, None)])
 def test_other_physical_parameters(oracle, lbm, monkeypatch, density, accel, omega, nx, ny, env):
     """Relaxation from under- to almost marginally stable over-relaxation, no forcing, strong forcing (the guard of the
-    first accelerate then refuses some cells), other densities: still bit-exact, persistent and per-step kernels."""
+    first accelerate then refuses some cells), other densities: still bit-exact -- per-step kernels (default), the
+    persistent cooperative kernel (LBM_B200_PERSISTENT=1) and the cluster kernel (256 x 64)."""
     if env is not None:
         monkeypatch.setenv("LBM_B200_PERSISTENT", env)
     rng = np.random.default_rng(int(omega * 100) + nx)
