@@ -57,7 +57,8 @@ const bool g_debug_sync = getenv("LBM_B200_DEBUG_SYNC") != nullptr;
     if (e_ != cudaSuccess) return fail(LBM_E_CUDA, "kernel %s failed: %s", name, cudaGetErrorString(e_)); \
   } while (0)
 
-constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation
+constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation: 64 ints (south, north, six sides) ...
+constexpr int kRowFlagsAt = 64;           // ... followed by 2 x tiles_y ints: per-tile-row flags of the west / east ghost columns
 constexpr size_t kStageBytes = 64u << 20;  // AoS staging chunk for upload/download
 constexpr int kClusterChunkSteps = 8192;  // timesteps per launch of the cluster-resident kernel
 constexpr int kPersistentMaxCtas = 1024;  // upper bound on the persistent kernel's grid
@@ -112,6 +113,7 @@ struct Slab {
   // 2-D blocks: the six further neighbours (lbm::SIDE_W .. SIDE_NE), own pointers where the partition wraps onto itself
   float *side_buf[6][2] = {};
   int *flag_to_side[6] = {};
+  int *flag_to_w_rows = nullptr, *flag_to_e_rows = nullptr;  // the west block's "from east" row flags, the east block's "from west"
   // launch configuration
   int kernel = 0;  // KERNEL_SCALAR / KERNEL_VEC4 / KERNEL_HYBRID
   int tiles_y = 1; // tile rows this slab sweeps = ceil((nyl + 2) / 8)
@@ -142,6 +144,7 @@ struct lbm_handle {
   int rows_alloc = 0; // storage rows per slab incl. the two ghost rows
   size_t lattice_floats = 0;
   size_t lattice_bytes = 0;
+  size_t flag_bytes = kFlagBytes;  // kFlagBytes + the row flags (2-D blocks)
   std::vector<Slab> slabs;
   bool multi = false;      // more than one slab in the ring (or a 2-D block partition): flags and halo pushes are on
   bool xghost = false;     // 2-D block partition: blocks keep ghost columns (lbm_create_grid)
@@ -279,7 +282,7 @@ int configure_launch(lbm_handle *h, Slab &s) {
 
 int alloc_slab(lbm_handle *h, Slab &s) {
   CUDA_TRY(cudaSetDevice(s.device));
-  const size_t total = 2 * h->lattice_bytes + kFlagBytes;
+  const size_t total = 2 * h->lattice_bytes + h->flag_bytes;
   cudaError_t e = cudaMalloc((void **)&s.base, total);
   if (e != cudaSuccess)
     return fail(LBM_E_NOMEM, "cudaMalloc of %zu bytes for a %d-row slab failed: %s", total, s.nyl,
@@ -287,7 +290,7 @@ int alloc_slab(lbm_handle *h, Slab &s) {
   s.buf[0] = reinterpret_cast<float *>(s.base);
   s.buf[1] = reinterpret_cast<float *>(s.base + h->lattice_bytes);
   s.flags = reinterpret_cast<int *>(s.base + 2 * h->lattice_bytes);
-  CUDA_TRY(cudaMemset(s.flags, 0, kFlagBytes));
+  CUDA_TRY(cudaMemset(s.flags, 0, h->flag_bytes));
   const size_t mask_bytes = (size_t)h->tiles_y * h->ntx * lbm::kTileMaskWords * sizeof(uint32_t);
   CUDA_TRY(cudaMalloc((void **)&s.mask, mask_bytes));
   CUDA_TRY(cudaMemset(s.mask, 0, mask_bytes));
@@ -362,6 +365,7 @@ void set_geometry(lbm_handle *h, int nx, int ny, int max_iters, float density, f
   h->lattice_floats = (size_t)h->tiles_y * h->ntx * lbm::kTileFloats;
   h->lattice_bytes = h->lattice_floats * sizeof(float);
   h->multi = ring > 1 || xghost;
+  h->flag_bytes = kFlagBytes + (xghost ? ((size_t)2 * h->tiles_y * sizeof(int) + 255) / 256 * 256 : 0);
   h->accel_row_global = ny - 2;
 }
 
@@ -402,13 +406,17 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   }
   a.flag_from_side = s.flags + 2;
   a.sdiag_ghost_row = s.south_ghost_row;
+  a.flag_from_w_rows = s.flags + kRowFlagsAt;
+  a.flag_from_e_rows = s.flags + kRowFlagsAt + h->tiles_y;
+  a.flag_to_w_rows = s.flag_to_w_rows;
+  a.flag_to_e_rows = s.flag_to_e_rows;
   return a;
 }
 
 template <typename K>
-cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, bool pdl, const lbm::SweepArgs &a) {
+cudaError_t launch_pdl(K kernel, dim3 grid, cudaStream_t stream, bool pdl, const lbm::SweepArgs &a) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.gridDim = grid;
   cfg.blockDim = dim3(32, lbm::kTileH, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
@@ -452,10 +460,12 @@ int launch_sweep(lbm_handle *h, Slab &s, int t, bool overlap) {
   const bool pdl = overlap && pdl_enabled;
   cudaError_t e;
   const int multi = h->xghost ? 2 : (h->multi ? 1 : 0);
+  // blocks: a 2-D grid (tile column, tile row); slabs: tiles in one dimension
+  const dim3 grid1((unsigned)s.grid, 1, 1), grid2((unsigned)s.ntx_sweep, (unsigned)s.tiles_y, 1);
 #define LBM_SWEEP(MODE)                                                                              \
-  (multi == 2   ? launch_pdl(lbm::sweep_kernel<MODE, 2>, s.grid, s.stream, pdl, a)                    \
-   : multi == 1 ? launch_pdl(lbm::sweep_kernel<MODE, 1>, s.grid, s.stream, pdl, a)                    \
-                : launch_pdl(lbm::sweep_kernel<MODE, 0>, s.grid, s.stream, pdl, a))
+  (multi == 2   ? launch_pdl(lbm::sweep_kernel<MODE, 2>, grid2, s.stream, pdl, a)                     \
+   : multi == 1 ? launch_pdl(lbm::sweep_kernel<MODE, 1>, grid1, s.stream, pdl, a)                     \
+                : launch_pdl(lbm::sweep_kernel<MODE, 0>, grid1, s.stream, pdl, a))
   if (s.kernel == KERNEL_VEC4) e = LBM_SWEEP(lbm::SWEEP_VEC4);
   else if (s.kernel == KERNEL_HYBRID) e = LBM_SWEEP(lbm::SWEEP_HYBRID);
   else e = LBM_SWEEP(lbm::SWEEP_SCALAR);
@@ -620,7 +630,7 @@ int wire_local_ring(lbm_handle *h) {
 int reset_counters(lbm_handle *h) {
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
-    CUDA_TRY(cudaMemsetAsync(s.flags, 0, kFlagBytes, s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.flags, 0, h->flag_bytes, s.stream));
     CUDA_TRY(cudaMemsetAsync(s.ticket, 0, 16 * sizeof(unsigned), s.stream));
     s.window_first = 0;
     s.window_count = 0;
@@ -762,6 +772,8 @@ int wire_local_grid(lbm_handle *h) {
         for (int b = 0; b < 2; ++b) s.side_buf[i][b] = nb.buf[b];
         s.flag_to_side[i] = nb.flags + 2 + sides[i].back;
       }
+      s.flag_to_w_rows = at(bx - 1, by).flags + kRowFlagsAt + h->tiles_y;  // its "from east" rows
+      s.flag_to_e_rows = at(bx + 1, by).flags + kRowFlagsAt;               // its "from west" rows
     }
   // peer access between every pair of distinct devices that are neighbours (8-neighbourhood)
   for (int by = 0; by < py; ++by)
@@ -793,6 +805,8 @@ int lbm_create_grid(lbm_handle **out, int nx, int ny, int max_iters, float densi
   int rc = check_problem(nx, ny, max_iters, py);
   if (rc) return rc;
   if (nx < px) return fail(LBM_E_ARG, "cannot cut %d columns into %d blocks", nx, px);
+  if ((ny / py + 3 + lbm::kTileH) / lbm::kTileH > 65535)
+    return fail(LBM_E_ARG, "blocks of %d rows exceed the 65535 tile rows of a launch grid: use more block rows", ny / py + 1);
   int ndev = 0;
   rc = lbm_device_count(&ndev);
   if (rc) return rc;
@@ -1277,7 +1291,8 @@ int lbm_run(lbm_handle *h, int iters) {
         lbm::publish_epoch_kernel<<<1, 1, 0, s.stream>>>(s.flag_to_south, s.flag_to_north, h->steps_done + 1);
         ++h->launches;
         if (h->xghost) {
-          lbm::publish_epoch_sides_kernel<<<1, 1, 0, s.stream>>>(side, h->steps_done + 1);
+          lbm::publish_epoch_sides_kernel<<<(std::max(s.tiles_y, 6) + 127) / 128, 128, 0, s.stream>>>(side, s.flag_to_w_rows, s.flag_to_e_rows,
+                                                                                                   s.tiles_y, h->steps_done + 1);
           ++h->launches;
         }
       }
