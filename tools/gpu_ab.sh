@@ -6,7 +6,7 @@ run() { # label lib args...
   local r=$(LBM_B200_LIB=$lib timeout 300 python bench.py --no-e2e --no-cpu-baseline "$@" 2>&1 | tail -1)
   echo "$label $(echo "$r" | python -c 'import sys,json
 try:
-    j=json.loads(sys.stdin.read()); print(j["config"]["kernel_variant"], j["value"], "MLUPS", round(j["ms_per_step"]*1000,2), "us/step", j["clocks"]["sm_mhz"], j["clocks"]["reasons"])
+    j=json.loads(sys.stdin.read()); print(j["detail"]["kernel_variant"], j["value"], "MLUPS", round(j["ms_per_step"]*1000,2), "us/step", j["clocks"]["sm_mhz"], j["clocks"]["reasons"])
 except Exception as e: print("FAILED", e)')" | tee -a $OUT/ab.txt
 }
 for rep in 1 2; do

@@ -7,7 +7,7 @@ one() { # label env... -- n
   local envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
   local n=$1
   env "${envs[@]}" python bench.py --no-e2e --no-cpu-baseline --nx $n --ny $n --steps 20000 --warmup 1000 > $OUT/tmp.log 2>&1
-  local us=$(tail -1 $OUT/tmp.log | python -c 'import sys,json; j=json.loads(sys.stdin.read()); print(j["config"]["kernel_variant"], round(j["ms_per_step"]*1000,2), "us/step", j["value"], "MLUPS")' 2>/dev/null)
+  local us=$(tail -1 $OUT/tmp.log | python -c 'import sys,json; j=json.loads(sys.stdin.read()); print(j["detail"]["kernel_variant"], round(j["ms_per_step"]*1000,2), "us/step", j["value"], "MLUPS")' 2>/dev/null)
   echo "$label ${n}x${n}: $us | $(grep 'persistent profile' $OUT/tmp.log | tail -1)" | tee -a $OUT/prof.txt
 }
 for n in 128 256 512 1024; do

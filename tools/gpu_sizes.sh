@@ -6,7 +6,7 @@ run() { # label, args...
   local r=$(timeout 300 python bench.py --steps 100 --warmup 10 --no-e2e --no-cpu-baseline "$@" 2>&1 | tail -1)
   echo "$label $(echo "$r" | python -c 'import sys,json
 try:
-    j=json.loads(sys.stdin.read()); print(j["value"], j["ms_per_step"], j["roofline"]["achieved"], j["config"]["kernel_variant"], j["clocks"]["reasons"])
+    j=json.loads(sys.stdin.read()); print(j["value"], j["ms_per_step"], j["roofline"]["achieved"], j["detail"]["kernel_variant"], j["clocks"]["reasons"])
 except Exception as e: print("FAILED", e)')" | tee -a $OUT/sizes.txt
 }
 for ny in 16384 8192 4096 2048 1024; do run "single_ny$ny" --ny $ny; done

@@ -7,7 +7,7 @@ run() { # label, env... -- args
   local r=$(env "${envs[@]}" timeout 300 python bench.py --no-e2e --no-cpu-baseline "$@" 2>&1 | tail -1)
   echo "$label $(echo "$r" | python -c 'import sys,json
 try:
-    j=json.loads(sys.stdin.read()); print(j["config"]["kernel_variant"], j["value"], "MLUPS", round(j["ms_per_step"]*1000,3), "us/step", j["roofline"]["achieved"], "GB/s")
+    j=json.loads(sys.stdin.read()); print(j["detail"]["kernel_variant"], j["value"], "MLUPS", round(j["ms_per_step"]*1000,3), "us/step", j["roofline"]["achieved"], "GB/s")
 except Exception as e: print("FAILED", e)')" | tee -a $OUT/small.txt
 }
 for n in 128 256 512 1024; do
