@@ -57,8 +57,7 @@ const bool g_debug_sync = getenv("LBM_B200_DEBUG_SYNC") != nullptr;
     if (e_ != cudaSuccess) return fail(LBM_E_CUDA, "kernel %s failed: %s", name, cudaGetErrorString(e_)); \
   } while (0)
 
-constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation: 64 ints (south, north, six sides) ...
-constexpr int kRowFlagsAt = 64;           // ... followed by 2 x tiles_y ints: per-tile-row flags of the west / east ghost columns
+constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation (south, north, six sides)
 constexpr size_t kStageBytes = 64u << 20;  // AoS staging chunk for upload/download
 constexpr int kClusterChunkSteps = 8192;  // timesteps per launch of the cluster-resident kernel
 constexpr int kPersistentMaxCtas = 1024;  // upper bound on the persistent kernel's grid
@@ -113,7 +112,6 @@ struct Slab {
   // 2-D blocks: the six further neighbours (lbm::SIDE_W .. SIDE_NE), own pointers where the partition wraps onto itself
   float *side_buf[6][2] = {};
   int *flag_to_side[6] = {};
-  int *flag_to_w_rows = nullptr, *flag_to_e_rows = nullptr;  // the west block's "from east" row flags, the east block's "from west"
   // launch configuration
   int kernel = 0;  // KERNEL_SCALAR / KERNEL_VEC4 / KERNEL_HYBRID
   int tiles_y = 1; // tile rows this slab sweeps = ceil((nyl + 2) / 8)
@@ -144,7 +142,7 @@ struct lbm_handle {
   int rows_alloc = 0; // storage rows per slab incl. the two ghost rows
   size_t lattice_floats = 0;
   size_t lattice_bytes = 0;
-  size_t flag_bytes = kFlagBytes;  // kFlagBytes + the row flags (2-D blocks)
+  size_t flag_bytes = kFlagBytes;
   std::vector<Slab> slabs;
   bool multi = false;      // more than one slab in the ring (or a 2-D block partition): flags and halo pushes are on
   bool xghost = false;     // 2-D block partition: blocks keep ghost columns (lbm_create_grid)
@@ -365,7 +363,6 @@ void set_geometry(lbm_handle *h, int nx, int ny, int max_iters, float density, f
   h->lattice_floats = (size_t)h->tiles_y * h->ntx * lbm::kTileFloats;
   h->lattice_bytes = h->lattice_floats * sizeof(float);
   h->multi = ring > 1 || xghost;
-  h->flag_bytes = kFlagBytes + (xghost ? ((size_t)2 * h->tiles_y * sizeof(int) + 255) / 256 * 256 : 0);
   h->accel_row_global = ny - 2;
 }
 
@@ -406,10 +403,6 @@ lbm::SweepArgs sweep_args(const lbm_handle *h, const Slab &s) {
   }
   a.flag_from_side = s.flags + 2;
   a.sdiag_ghost_row = s.south_ghost_row;
-  a.flag_from_w_rows = s.flags + kRowFlagsAt;
-  a.flag_from_e_rows = s.flags + kRowFlagsAt + h->tiles_y;
-  a.flag_to_w_rows = s.flag_to_w_rows;
-  a.flag_to_e_rows = s.flag_to_e_rows;
   return a;
 }
 
@@ -455,6 +448,20 @@ int launch_sweep(lbm_handle *h, Slab &s, int t, bool overlap) {
   if (s.window_count == 0) s.window_first = t;
   lbm::SweepArgs a = sweep_args(h, s);
   a.t = t;
+  if (h->xghost) {
+    // whose completion this launch announces (ghost columns / corners, see sweep_kernel): the slab launched just before it in
+    // this stream -- the previous slab on the stream at this step, or the stream's last slab at the previous step.  The order
+    // is the fixed one of enqueue_steps, so this is static (and the same inside a captured graph, with relative steps).
+    const Slab *pred = nullptr, *last = nullptr;
+    for (const Slab &o : h->slabs) {
+      if (o.stream != s.stream) continue;
+      if (&o < &s) pred = &o;
+      last = &o;
+    }
+    const Slab *who = pred ? pred : last;
+    for (int i = 0; i < 6; ++i) a.pub_flag[i] = who->flag_to_side[i];
+    a.pub_epoch = pred ? t + 2 : t + 1;  // (pred ran step t: its epoch t + 2; the last slab ran step t - 1: t + 1)
+  }
   a.partials = s.partials + (size_t)s.window_count * s.grid;
   ++s.window_count;
   const bool pdl = overlap && pdl_enabled;
@@ -772,8 +779,6 @@ int wire_local_grid(lbm_handle *h) {
         for (int b = 0; b < 2; ++b) s.side_buf[i][b] = nb.buf[b];
         s.flag_to_side[i] = nb.flags + 2 + sides[i].back;
       }
-      s.flag_to_w_rows = at(bx - 1, by).flags + kRowFlagsAt + h->tiles_y;  // its "from east" rows
-      s.flag_to_e_rows = at(bx + 1, by).flags + kRowFlagsAt;               // its "from west" rows
     }
   // peer access between every pair of distinct devices that are neighbours (8-neighbourhood)
   for (int by = 0; by < py; ++by)
@@ -1291,8 +1296,7 @@ int lbm_run(lbm_handle *h, int iters) {
         lbm::publish_epoch_kernel<<<1, 1, 0, s.stream>>>(s.flag_to_south, s.flag_to_north, h->steps_done + 1);
         ++h->launches;
         if (h->xghost) {
-          lbm::publish_epoch_sides_kernel<<<(std::max(s.tiles_y, 6) + 127) / 128, 128, 0, s.stream>>>(side, s.flag_to_w_rows, s.flag_to_e_rows,
-                                                                                                   s.tiles_y, h->steps_done + 1);
+          lbm::publish_epoch_sides_kernel<<<1, 1, 0, s.stream>>>(side, h->steps_done + 1);
           ++h->launches;
         }
       }
