@@ -166,7 +166,7 @@ int run_map(const Options &o) {
   // one pixel per `scale` x `scale` cells, at most 2048 pixels a side; row 0 of the grid at the bottom of the picture
   const int scale = std::max(1, (std::max(o.width, o.height) + 2047) / 2048);
   const int w = (o.width + scale - 1) / scale, h = (o.height + scale - 1) / scale;
-  static const uint8_t colours[8][3] = {{0x23, 0x25, 0x42}, {0x72, 0x1D, 0x3A}, {0xF4, 0xA3, 0x16}, {0x2A, 0x9D, 0x8F},
+  static const uint8_t colours[8][3] = {{0x1F, 0x3A, 0x5F}, {0x8C, 0x2F, 0x39}, {0xE0, 0x9F, 0x3E}, {0x2A, 0x9D, 0x8F},
                                         {0x45, 0x7B, 0x9D}, {0xE7, 0x6F, 0x51}, {0x8A, 0xB1, 0x7D}, {0x6D, 0x59, 0x7A}};
   std::vector<uint8_t> rgb((size_t)w * h * 3);
   const std::vector<part::Block> bl = part::blocks(o.width, o.height, px, py);

@@ -145,3 +145,20 @@ def test_runner_accepts_the_cxxopts_spellings(lbm, tmp_path):
     for bad in (["-nd", "1"], ["--debug=maybe"], ["-n"], ["--num-gpus"], ["-x"], ["stray"], ["--prepare"], ["-n", "two"]):
         r = run(*bad)
         assert r.returncode != 0 and usage in r.stderr, bad
+
+
+@pytest.mark.gpu
+def test_numa_helpers_are_best_effort(lbm):
+    """lbm_host_alloc_near / lbm_bind_thread_near: pinned memory near a GPU and the GPU-local CPU set, from sysfs.  On a flat
+    or virtualised topology they degrade to a plain pinned allocation / a refusal code -- never a crash."""
+    import ctypes
+    import numpy as np
+    ptr = lbm.host_alloc(1 << 20, 0)
+    assert ptr
+    a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(1 << 20,))
+    a[:] = 7
+    assert int(a.sum()) == 7 << 20
+    lbm.lib.lbm_host_free(ptr)
+    rc = lbm.lib.lbm_bind_thread_near(0)
+    assert rc >= 0 or rc == -3  # the NUMA node, or LBM_E_STATE when sysfs has no local_cpulist / the call is refused
+    assert lbm.lib.lbm_bind_thread_near(999) < 0
