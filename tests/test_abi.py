@@ -159,6 +159,10 @@ def test_numa_helpers_are_best_effort(lbm):
     a[:] = 7
     assert int(a.sum()) == 7 << 20
     lbm.lib.lbm_host_free(ptr)
-    rc = lbm.lib.lbm_bind_thread_near(0)
-    assert rc >= 0 or rc == -3  # the NUMA node, or LBM_E_STATE when sysfs has no local_cpulist / the call is refused
-    assert lbm.lib.lbm_bind_thread_near(999) < 0
+    before = os.sched_getaffinity(0)
+    try:
+        rc = lbm.lib.lbm_bind_thread_near(0)
+        assert rc >= 0 or rc == -3  # the NUMA node, or LBM_E_STATE when sysfs has no local_cpulist / the call is refused
+        assert lbm.lib.lbm_bind_thread_near(999) < 0
+    finally:
+        os.sched_setaffinity(0, before)  # the rest of the session keeps all its cores
