@@ -1756,6 +1756,8 @@ int lbm_pipeline_info(lbm_pipeline *p, int *bands, int *band_rows, int *margin_r
 
 int lbm_solve_host(int nx, int ny, int iters, float density, float accel, float omega, int device, const float *cells_in,
                    const uint8_t *obstacles, float *cells_out, float *av_vels, double *elapsed_ms) {
+  if (!cells_in || !obstacles || !cells_out) return fail(LBM_E_ARG, "null argument");
+  if (cells_in == cells_out) return fail(LBM_E_ARG, "cells_out must not alias cells_in");
   const double t_begin = now_ms();
   lbm_pipeline *p = nullptr;
   int rc = lbm_pipeline_create(&p, nx, ny, iters, density, accel, omega, device);

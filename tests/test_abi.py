@@ -166,3 +166,26 @@ def test_numa_helpers_are_best_effort(lbm):
         assert lbm.lib.lbm_bind_thread_near(999) < 0
     finally:
         os.sched_setaffinity(0, before)  # the rest of the session keeps all its cores
+
+
+def test_new_entry_points_validate_before_touching_cuda(lbm, tmp_path):
+    """lbm_load, lbm_create_grid, lbm_pipeline_create and lbm_solve_host reject bad input with LBM_E_ARG (-1) and a message
+    without needing a device; with good input and no device they fail with LBM_E_CUDA (-2), never silently."""
+    import ctypes
+    h = ctypes.c_void_p()
+    bad = tmp_path / "bad.lbm"
+    bad.write_bytes(b"x" * 100)
+    assert lbm.lib.lbm_load(ctypes.byref(h), str(bad).encode(), 1) == -1 and b"not a prepared-solver file" in lbm.lib.lbm_last_error()
+    assert lbm.lib.lbm_load(ctypes.byref(h), str(tmp_path / "none.lbm").encode(), 1) == -1 and not h.value
+    assert lbm.lib.lbm_create_grid(ctypes.byref(h), 64, 64, 1, 0.1, 0.005, 1.85, 0, 2, None) == -1
+    assert lbm.lib.lbm_create_grid(ctypes.byref(h), 8, 64, 1, 0.1, 0.005, 1.85, 16, 1, None) == -1 and b"columns" in lbm.lib.lbm_last_error()
+    p = ctypes.c_void_p()
+    assert lbm.lib.lbm_pipeline_create(ctypes.byref(p), 0, 64, 1, 0.1, 0.005, 1.85, 0) == -1 and not p.value
+    assert lbm.lib.lbm_pipeline_solve(None, None, None, None, None) == -1
+    lbm.lib.lbm_pipeline_destroy(None)  # harmless
+    assert lbm.lib.lbm_solve_host(64, 64, 1, 0.1, 0.005, 1.85, 0, None, None, None, None, None) == -1
+    assert lbm.lib.lbm_save(None, b"x") == -1 and lbm.lib.lbm_ipc_disconnect(None) == -1
+    if lbm.device_count() == 0:
+        assert lbm.lib.lbm_create_grid(ctypes.byref(h), 64, 64, 1, 0.1, 0.005, 1.85, 1, 1, None) == -2
+        assert lbm.lib.lbm_pipeline_create(ctypes.byref(p), 64, 64, 1, 0.1, 0.005, 1.85, 0) == -2
+        assert b"CUDA" in lbm.lib.lbm_last_error() or b"device" in lbm.lib.lbm_last_error()
