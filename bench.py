@@ -575,7 +575,7 @@ def main():
                "h2d_gbs_per_gpu": round((nbytes_cells + nbytes_obst) / t_up / 1e9, 1),
                "d2h_gbs_per_gpu": round(nbytes_cells / t_down / 1e9, 1)}
         slabs.close_ring(s2, dist)
-        if world == 1:
+        if world == 1 and nbytes_cells <= 12e9:  # (a second pinned lattice-sized host buffer: not for the 38 GB weak-scaling grid)
             # The same job as ONE call, lbm_pipeline_solve: the grid is solved band by band (a band plus K + a few margin rows
             # is all that K steps of it depend on), so uploads, sweeps and downloads of different bands overlap and PCIe
             # carries data both ways at once.  Same result (checked below against the sequential job's), fewer seconds.
