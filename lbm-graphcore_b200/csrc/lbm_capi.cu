@@ -176,6 +176,7 @@ const void *cluster_kernel(int nx, int cells, int cpt) {
   if (nx == NX && cells == CELLS && cpt == CPT) return (const void *)lbm::sweep_cluster_kernel<NX, CELLS, CPT>;
   LBM_CK(128, 1024, 4) LBM_CK(128, 1024, 2) LBM_CK(128, 512, 4) LBM_CK(128, 512, 2) LBM_CK(128, 512, 1) LBM_CK(128, 256, 1)
   LBM_CK(256, 1024, 4) LBM_CK(256, 1024, 2) LBM_CK(256, 512, 4) LBM_CK(256, 512, 2) LBM_CK(256, 512, 1)
+  LBM_CK(512, 1024, 2) LBM_CK(512, 2048, 4)
 #undef LBM_CK
   return nullptr;
 }
@@ -221,24 +222,24 @@ int configure_launch(lbm_handle *h, Slab &s) {
       s.persistent_grid = ctas;
     }
   }
-  // The smallest inputs (nx = 128 or 256, a few dozen K cells) keep both lattices in the distributed shared memory of
-  // thread-block clusters (sweep_cluster_kernel): CTAs of 512 cells (1024 if that many CTAs cannot be co-resident; 256 on
-  // request) -- one cell per thread (two at 1024), the largest cluster size <= 16 that divides the CTA count and fits.  LBM_B200_CLUSTER=0 disables; LBM_B200_CLUSTER_CELLS /
+  // The smallest inputs (nx = 128, 256 or 512, up to ~300 K cells) keep both lattices in the distributed shared memory of
+  // thread-block clusters (sweep_cluster_kernel): CTAs of 512 cells (1024 or, for nx = 512, 2048 if that many CTAs cannot be
+  // co-resident or do not hold two full rows; 256 on request) -- one cell per thread (two at 1024, four at 2048), the largest cluster size <= 16 that divides the CTA count and fits.  LBM_B200_CLUSTER=0 disables; LBM_B200_CLUSTER_CELLS /
   // _CPT / _SIZE pin the shape (tuning runs).
   s.cluster_ctas = 0;
   const int want_cluster = getenv("LBM_B200_CLUSTER") ? atoi(getenv("LBM_B200_CLUSTER")) : 1;
   if (!h->multi && want_cluster != 0 && want == -1 && !getenv("LBM_B200_KERNEL") && !s.cluster_refused &&
-      (h->nx == 128 || h->nx == 256)) {
+      (h->nx == 128 || h->nx == 256 || h->nx == 512)) {
     CUDA_TRY(cudaSetDevice(s.device));
     const int env_cells = getenv("LBM_B200_CLUSTER_CELLS") ? atoi(getenv("LBM_B200_CLUSTER_CELLS")) : 0;
     const int env_cpt = getenv("LBM_B200_CLUSTER_CPT") ? atoi(getenv("LBM_B200_CLUSTER_CPT")) : 0;
     const int env_cs = getenv("LBM_B200_CLUSTER_SIZE") ? atoi(getenv("LBM_B200_CLUSTER_SIZE")) : 0;
     // smallest CTAs first: the update is issue-bound per SM, so the more SMs share a lattice the shorter a step
     // (profiles/r02b_small_grids_cluster_v3.txt: 128^2 1.31 / 0.86 us per step with 1024 / 512 cells per CTA)
-    for (int cells : {512, 1024, 256}) {  // (256-cell CTAs measured no faster than 512: twice the SMs for the same step time)
+    for (int cells : {512, 1024, 2048, 256}) {  // (256-cell CTAs measured no faster than 512: twice the SMs for the same step time)
       if (s.cluster_ctas > 0) break;
       if (env_cells && env_cells != cells) continue;
-      const int rows = cells / h->nx, cpt = env_cpt ? env_cpt : (cells == 1024 ? 2 : 1);
+      const int rows = cells / h->nx, cpt = env_cpt ? env_cpt : (cells == 2048 ? 4 : cells == 1024 ? 2 : 1);
       if (rows < 2 || s.nyl % rows != 0) continue;
       const int G = s.nyl / rows;
       const void *fn = cluster_kernel(h->nx, cells, cpt);

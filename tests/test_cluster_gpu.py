@@ -36,9 +36,13 @@ SHAPES = [(128, 128),   # 1024-cell CTAs: one cluster of 16, the y-wrap closes i
           (128, 136),   # G = 17 (seventeen clusters of ONE CTA: every edge goes through the global halo) / 34
           (256, 8),
           (128, 8)]     # G = 1 / 2: a CTA that is its own neighbour on both sides
+WIDE = [(512, 512),     # 2048-cell CTAs (four rows of 512, four cells per thread): 128 CTAs
+        (512, 64),      # 1024-cell CTAs (two rows, two cells per thread): 32 CTAs
+        (512, 296),     # 148 CTAs of 1024 cells: every SM
+        (512, 12)]      # G = 6
 
 
-@pytest.mark.parametrize("nx,ny", SHAPES)
+@pytest.mark.parametrize("nx,ny", SHAPES + WIDE)
 def test_cluster_kernel_bit_exact(oracle, lbm, nx, ny):
     _check(oracle, lbm, nx, ny, 45)
 
