@@ -175,6 +175,17 @@ int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density,
 typedef struct lbm_pipeline lbm_pipeline;
 int lbm_pipeline_create(lbm_pipeline **out, int nx, int ny, int iters, float density, float accel, float omega, int device);
 int lbm_pipeline_solve(lbm_pipeline *p, const float *cells_in, const uint8_t *obstacles, float *cells_out, float *av_vels);
+/* The same for ONE RANK of a multi-process job: the pipeline solves the WINDOW of global rows [row_begin, row_begin +
+ * row_count) (row_count a multiple of 8) of the nx x ny grid.  cells_window / obstacles_window hold the initial state of the
+ * window AND of `margin_rows` (lbm_pipeline_info) rows below and above it, contiguously, in global row order with periodic
+ * wrap -- (row_count + 2 * margin_rows) rows; the rows outside the window belong to the neighbouring ranks, which exchange
+ * them once (host to host) before the job.  In return no rank waits for another during the job: `iters` timesteps of the
+ * window depend on nothing else.  cells_out receives the window's row_count rows; tot_u[iters] and *free_cells are this
+ * rank's part of the av_vels sums, to be combined in rank order like lbm_download_tot_u's. */
+int lbm_pipeline_create_window(lbm_pipeline **out, int nx, int ny, int row_begin, int row_count, int iters, float density,
+                               float accel, float omega, int device);
+int lbm_pipeline_solve_window(lbm_pipeline *p, const float *cells_window, const uint8_t *obstacles_window, float *cells_out,
+                              double *tot_u, long long *free_cells);
 /* how the job is cut (1 band = not banded) and the wall time of the last solve; any pointer may be NULL */
 int lbm_pipeline_info(lbm_pipeline *p, int *bands, int *band_rows, int *margin_rows, double *last_ms);
 void lbm_pipeline_destroy(lbm_pipeline *p);

@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_host_alloc_near", "lbm_bind_thread_near", "lbm_create_rank", "lbm_ipc_blob_bytes",
     "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_problem", "lbm_create_grid", "lbm_partition", "lbm_block_info", "lbm_solve_host", "lbm_pipeline_create", "lbm_pipeline_solve",
-    "lbm_pipeline_info", "lbm_pipeline_destroy", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
+    "lbm_pipeline_info", "lbm_pipeline_destroy", "lbm_pipeline_create_window", "lbm_pipeline_solve_window", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
 )
 
 
@@ -99,6 +99,8 @@ def _load() -> ctypes.CDLL:
                                    P(ctypes.c_double)]
     lib.lbm_pipeline_create.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int]
     lib.lbm_pipeline_solve.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.lbm_pipeline_create_window.argtypes = [P(c_void_p), c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int]
+    lib.lbm_pipeline_solve_window.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(ctypes.c_longlong)]
     lib.lbm_pipeline_info.argtypes = [c_void_p, P(c_int), P(c_int), P(c_int), P(ctypes.c_double)]
     lib.lbm_pipeline_destroy.argtypes = [c_void_p]
     lib.lbm_pipeline_destroy.restype = None
@@ -133,11 +135,34 @@ def host_alloc(nbytes: int, device: int | None = None) -> int:
 class Pipeline:
     """lbm_pipeline: whole jobs (upload, `iters` timesteps, download) of one problem shape, band-pipelined over PCIe."""
 
-    def __init__(self, params: Params, iters: int | None = None, device: int = 0):
+    def __init__(self, params: Params, iters: int | None = None, device: int = 0, window: tuple[int, int] | None = None):
+        """window = (row_begin, row_count): one rank's slab of the grid (lbm_pipeline_create_window)."""
         p = params
-        self.params, self.iters = p, (p.max_iters if iters is None else iters)
+        self.params, self.iters, self.window = p, (p.max_iters if iters is None else iters), window
         self._p = ctypes.c_void_p()
-        _check(lib.lbm_pipeline_create(ctypes.byref(self._p), p.nx, p.ny, self.iters, p.density, p.accel, p.omega, device))
+        if window is None:
+            _check(lib.lbm_pipeline_create(ctypes.byref(self._p), p.nx, p.ny, self.iters, p.density, p.accel, p.omega, device))
+        else:
+            _check(lib.lbm_pipeline_create_window(ctypes.byref(self._p), p.nx, p.ny, window[0], window[1], self.iters, p.density,
+                                                  p.accel, p.omega, device))
+
+    def solve_window_raw(self, cells_ptr: int, obstacles_ptr: int, cells_out_ptr: int):
+        """One rank's job: returns (tot_u float64[iters], free_cells) of the window."""
+        tot = np.zeros(max(self.iters, 1), dtype=np.float64)
+        free = ctypes.c_longlong()
+        _check(lib.lbm_pipeline_solve_window(self._p, cells_ptr, obstacles_ptr, cells_out_ptr, tot.ctypes.data, ctypes.byref(free)))
+        return tot[: self.iters], free.value
+
+    def solve_window(self, cells: np.ndarray, obstacles: np.ndarray):
+        """cells / obstacles: the WHOLE grid (convenience for tests): the window plus its margins is cut out here."""
+        r0, n = self.window
+        m, ny = self.info["margin_rows"], self.params.ny
+        idx = np.arange(r0 - m, r0 + n + m) % ny
+        win_c = np.ascontiguousarray(cells[idx], dtype=np.float32)
+        win_o = np.ascontiguousarray(obstacles[idx]).astype(np.uint8, copy=False)
+        out = np.empty((n, self.params.nx, NSPEEDS), dtype=np.float32)
+        tot, free = self.solve_window_raw(win_c.ctypes.data, win_o.ctypes.data, out.ctypes.data)
+        return out, tot, free
 
     def solve_raw(self, cells_in_ptr: int, obstacles_ptr: int, cells_out_ptr: int, av_vels_ptr: int | None) -> None:
         _check(lib.lbm_pipeline_solve(self._p, cells_in_ptr, obstacles_ptr, cells_out_ptr, av_vels_ptr))

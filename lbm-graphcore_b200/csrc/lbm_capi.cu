@@ -1570,6 +1570,11 @@ int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density,
 
 struct lbm_pipeline {
   int nx = 0, ny = 0, iters = 0, device = 0;
+  // the rows this pipeline solves: all of them, or a WINDOW [row0, row0 + rows) of the global grid (one rank's slab).  A
+  // window's input buffers start `margin` rows below row0 and end `margin` rows above its last row: the caller supplies the
+  // initial state of those rows too (they belong to its neighbours), and no rank ever waits for another.
+  bool window = false;
+  int row0 = 0, rows = 0;
   float density = 0, accel = 0, omega = 0;
   bool banded = false;
   int margin = 0, band_rows = 0, nbands = 1, workers = 1;
@@ -1597,10 +1602,11 @@ struct BandJob {
 int solve_band(lbm_pipeline *p, lbm_handle *h, BandJob &job, int b) {
   static const bool trace = getenv("LBM_B200_SOLVE_TRACE") != nullptr;
   const int nx = p->nx, ny = p->ny, M = p->margin;
-  const int r0 = b * p->band_rows, rows = std::min(p->band_rows, ny - r0), total = rows + 2 * M;
+  // band b = rows [r0, r0 + rows) of the pipeline's own rows (= of the grid unless it solves a window)
+  const int r0 = b * p->band_rows, rows = std::min(p->band_rows, p->rows - r0), total = rows + 2 * M;
   Slab &s = h->slabs[0];
-  // the band's rows -M .. rows + M - 1 are global rows r0 - M ... (periodic); the driven row may or may not be among them
-  const int first = ((r0 - M) % ny + ny) % ny;
+  // the band's rows -M .. rows + M - 1 are global rows row0 + r0 - M ... (periodic); the driven row may or may not be among them
+  const int first = ((p->row0 + r0 - M) % ny + ny) % ny;
   const int arow = ((ny - 2 - first) % ny + ny) % ny;
   h->accel_row_global = (ny >= 2 && arow < total) ? arow : -1;
   s.tot_ty_lo = (M + 1) / lbm::kTileH;
@@ -1613,10 +1619,14 @@ int solve_band(lbm_pipeline *p, lbm_handle *h, BandJob &job, int b) {
     std::lock_guard<std::mutex> lock(p->up);
     t_a = now_ms();
     rc = reset_counters(h);
-    for (int done = 0; done < total && rc == LBM_OK;) {  // contiguous pieces of the periodic row range
-      const int g = (first + done) % ny, n = std::min(total - done, ny - g);
-      rc = upload_rows(h, done, n, job.cells_in + (size_t)g * nx * lbm::kSpeeds, job.obstacles + (size_t)g * nx);
-      done += n;
+    if (p->window) {  // the caller's window is contiguous and starts M rows below the pipeline's first row
+      rc = rc ? rc : upload_rows(h, 0, total, job.cells_in + (size_t)r0 * nx * lbm::kSpeeds, job.obstacles + (size_t)r0 * nx);
+    } else {
+      for (int done = 0; done < total && rc == LBM_OK;) {  // contiguous pieces of the periodic row range
+        const int g = (first + done) % ny, n = std::min(total - done, ny - g);
+        rc = upload_rows(h, done, n, job.cells_in + (size_t)g * nx * lbm::kSpeeds, job.obstacles + (size_t)g * nx);
+        done += n;
+      }
     }
     if (rc == LBM_OK) rc = drain_all(h);
     if (rc == LBM_OK) rc = finish_upload(h);
@@ -1651,33 +1661,45 @@ void lbm_pipeline_destroy(lbm_pipeline *p) {
   delete p;
 }
 
-int lbm_pipeline_create(lbm_pipeline **out, int nx, int ny, int iters, float density, float accel, float omega, int device) {
+}  // extern "C"
+namespace {
+
+// window == false: the whole grid (row0 = 0, rows = ny)
+int pipeline_create(lbm_pipeline **out, int nx, int ny, bool window, int row0, int rows, int iters, float density, float accel,
+                    float omega, int device) {
   if (!out) return fail(LBM_E_ARG, "null argument");
   *out = nullptr;
   int rc = check_problem(nx, ny, iters, 1);
   if (rc) return rc;
+  if (window && (row0 < 0 || rows < 1 || row0 + rows > ny)) return fail(LBM_E_ARG, "window [%d, %d) is not inside 0..%d", row0, row0 + rows, ny);
+  if (window && rows % lbm::kTileH != 0) return fail(LBM_E_ARG, "a window must be a multiple of %d rows (got %d)", lbm::kTileH, rows);
   lbm_pipeline *p = new (std::nothrow) lbm_pipeline();
   if (!p) return fail(LBM_E_NOMEM, "out of host memory");
   p->nx = nx; p->ny = ny; p->iters = iters; p->device = device;
   p->density = density; p->accel = accel; p->omega = omega;
+  p->window = window; p->row0 = row0; p->rows = rows;
   // the margin: >= iters rows, and M + 1 a multiple of the tile height so that a band is whole tile rows of its solver
   p->margin = ((std::max(iters, 1) + 1 + lbm::kTileH - 1) / lbm::kTileH) * lbm::kTileH - 1;
-  p->band_rows = (int)std::max<long long>(lbm::kTileH, kSolveBandCells / nx / lbm::kTileH * lbm::kTileH);
+  const int min_band = (8 * p->margin + lbm::kTileH - 1) / lbm::kTileH * lbm::kTileH;  // margins at most a quarter of the upload
+  long long want = std::max<long long>(lbm::kTileH, kSolveBandCells / nx / lbm::kTileH * lbm::kTileH);
+  if (window) want = std::min<long long>(want, std::max(lbm::kTileH, rows / 4 / lbm::kTileH * lbm::kTileH));  // a slab: at least four bands
+  p->band_rows = (int)want;
   if (const char *e = getenv("LBM_B200_BAND_ROWS")) p->band_rows = std::max(lbm::kTileH, atoi(e) / lbm::kTileH * lbm::kTileH);  // tests
-  // bands pay when the margins are a small part of a band and there are enough bands to overlap
-  p->banded = ny % lbm::kTileH == 0 && p->band_rows >= 8 * p->margin && ny >= 4 * p->band_rows && !getenv("LBM_B200_NO_BANDS");
+  else if (window) p->band_rows = std::min(rows, std::max(p->band_rows, min_band));
+  // bands pay when the margins are a small part of a band and there are enough bands to overlap; a window has no other way
+  p->banded = window || (ny % lbm::kTileH == 0 && p->band_rows >= min_band && ny >= 4 * p->band_rows && !getenv("LBM_B200_NO_BANDS"));
   if (!p->banded) {
     rc = lbm_create_on_devices(&p->whole, nx, ny, iters, density, accel, omega, 1, &device);
     if (rc) { lbm_pipeline_destroy(p); return rc; }
     *out = p;
     return LBM_OK;
   }
-  p->nbands = (ny + p->band_rows - 1) / p->band_rows;
+  p->nbands = (rows + p->band_rows - 1) / p->band_rows;
   p->workers = std::min(kSolveWorkers, p->nbands);
   if (const char *e = getenv("LBM_B200_SOLVE_WORKERS")) p->workers = std::max(1, std::min(atoi(e), p->nbands));
-  const int last_rows = ny - (p->nbands - 1) * p->band_rows;
-  auto band_solver = [&](int rows, lbm_handle **slot) {
-    int r = lbm_create_on_devices(slot, nx, rows + 2 * p->margin, iters, density, accel, omega, 1, &device);
+  const int last_rows = rows - (p->nbands - 1) * p->band_rows;
+  auto band_solver = [&](int band, lbm_handle **slot) {
+    int r = lbm_create_on_devices(slot, nx, band + 2 * p->margin, iters, density, accel, omega, 1, &device);
     if (r == LBM_OK) {  // bands take the plain per-step kernel (a cached graph would bake in one band's driven row)
       (*slot)->slabs[0].persistent_grid = 0;
       (*slot)->slabs[0].cluster_ctas = 0;
@@ -1697,8 +1719,52 @@ int lbm_pipeline_create(lbm_pipeline **out, int nx, int ny, int iters, float den
   return LBM_OK;
 }
 
+// all bands; tot[t] = the per-step sums of the bands added in band order, free_cells = non-obstacle cells of the pipeline's rows
+int pipeline_run(lbm_pipeline *p, const float *cells_in, const uint8_t *obstacles, float *cells_out, std::vector<double> &tot,
+                 long long &free_cells) {
+  BandJob job{};
+  job.cells_in = cells_in; job.obstacles = obstacles; job.cells_out = cells_out;
+  job.tot.resize(p->nbands);
+  job.free_cells.assign(p->nbands, 0);
+  job.t_begin = now_ms();
+  std::vector<int> codes(p->workers, LBM_OK);
+  std::vector<std::string> messages(p->workers);
+  std::vector<std::thread> threads;
+  for (int w = 0; w < p->workers; ++w)
+    threads.emplace_back([&, w]() {
+      for (int b = w; b < p->nbands && codes[w] == LBM_OK; b += p->workers) {
+        const int rows = std::min(p->band_rows, p->rows - b * p->band_rows);
+        lbm_handle *h = rows == p->band_rows ? p->full[w] : p->last[w];
+        const int r = solve_band(p, h, job, b);
+        if (r != LBM_OK) { codes[w] = r; messages[w] = g_last_error; }
+      }
+    });
+  for (std::thread &t : threads) t.join();
+  for (int w = 0; w < p->workers; ++w)
+    if (codes[w] != LBM_OK) return fail(codes[w], "band solver: %s", messages[w].c_str());
+  free_cells = 0;
+  for (long long f : job.free_cells) free_cells += f;
+  tot.assign((size_t)p->iters, 0.0);
+  for (int t = 0; t < p->iters; ++t)
+    for (int b = 0; b < p->nbands; ++b) tot[t] += job.tot[b][t];  // band order
+  return LBM_OK;
+}
+
+}  // namespace
+extern "C" {
+
+int lbm_pipeline_create(lbm_pipeline **out, int nx, int ny, int iters, float density, float accel, float omega, int device) {
+  return pipeline_create(out, nx, ny, false, 0, ny, iters, density, accel, omega, device);
+}
+
+int lbm_pipeline_create_window(lbm_pipeline **out, int nx, int ny, int row_begin, int row_count, int iters, float density,
+                               float accel, float omega, int device) {
+  return pipeline_create(out, nx, ny, true, row_begin, row_count, iters, density, accel, omega, device);
+}
+
 int lbm_pipeline_solve(lbm_pipeline *p, const float *cells_in, const uint8_t *obstacles, float *cells_out, float *av_vels) {
   if (!p || !cells_in || !obstacles || !cells_out) return fail(LBM_E_ARG, "null argument");
+  if (p->window) return fail(LBM_E_STATE, "a window pipeline returns partial sums: use lbm_pipeline_solve_window");
   if (cells_in == cells_out) return fail(LBM_E_ARG, "cells_out must not alias cells_in");
   const double t_begin = now_ms();
   int rc = LBM_OK;
@@ -1710,37 +1776,34 @@ int lbm_pipeline_solve(lbm_pipeline *p, const float *cells_in, const uint8_t *ob
     return rc;
   }
   try {
-    BandJob job{};
-    job.cells_in = cells_in; job.obstacles = obstacles; job.cells_out = cells_out;
-    job.tot.resize(p->nbands);
-    job.free_cells.assign(p->nbands, 0);
-    job.t_begin = t_begin;
-    std::vector<int> codes(p->workers, LBM_OK);
-    std::vector<std::string> messages(p->workers);
-    std::vector<std::thread> threads;
-    for (int w = 0; w < p->workers; ++w)
-      threads.emplace_back([&, w]() {
-        for (int b = w; b < p->nbands && codes[w] == LBM_OK; b += p->workers) {
-          const int rows = std::min(p->band_rows, p->ny - b * p->band_rows);
-          lbm_handle *h = rows == p->band_rows ? p->full[w] : p->last[w];
-          const int r = solve_band(p, h, job, b);
-          if (r != LBM_OK) { codes[w] = r; messages[w] = g_last_error; }
-        }
-      });
-    for (std::thread &t : threads) t.join();
-    for (int w = 0; w < p->workers; ++w)
-      if (codes[w] != LBM_OK) return fail(codes[w], "band solver: %s", messages[w].c_str());
-    if (av_vels) {
-      long long free_cells = 0;
-      for (long long f : job.free_cells) free_cells += f;
-      for (int t = 0; t < p->iters; ++t) {
-        double tot = 0.0;
-        for (int b = 0; b < p->nbands; ++b) tot += job.tot[b][t];  // band order
-        av_vels[t] = (float)tot / (float)free_cells;                // main/LastChance.cpp:266
-      }
-    }
+    std::vector<double> tot;
+    long long free_cells = 0;
+    rc = pipeline_run(p, cells_in, obstacles, cells_out, tot, free_cells);
+    if (rc) return rc;
+    if (av_vels)
+      for (int t = 0; t < p->iters; ++t) av_vels[t] = (float)tot[t] / (float)free_cells;  // main/LastChance.cpp:266
   } catch (const std::exception &e) {  // thread or host-memory exhaustion: nothing may throw across the ABI
     return fail(LBM_E_NOMEM, "lbm_pipeline_solve: %s", e.what());
+  }
+  p->last_ms = now_ms() - t_begin;
+  return LBM_OK;
+}
+
+int lbm_pipeline_solve_window(lbm_pipeline *p, const float *cells_window, const uint8_t *obstacles_window, float *cells_out,
+                              double *tot_u, long long *free_cells) {
+  if (!p || !cells_window || !obstacles_window || !cells_out) return fail(LBM_E_ARG, "null argument");
+  if (!p->window) return fail(LBM_E_STATE, "not a window pipeline (lbm_pipeline_create_window)");
+  const double t_begin = now_ms();
+  try {
+    std::vector<double> tot;
+    long long free_count = 0;
+    int rc = pipeline_run(p, cells_window, obstacles_window, cells_out, tot, free_count);
+    if (rc) return rc;
+    if (tot_u)
+      for (int t = 0; t < p->iters; ++t) tot_u[t] = tot[t];
+    if (free_cells) *free_cells = free_count;
+  } catch (const std::exception &e) {
+    return fail(LBM_E_NOMEM, "lbm_pipeline_solve_window: %s", e.what());
   }
   p->last_ms = now_ms() - t_begin;
   return LBM_OK;
@@ -1749,7 +1812,7 @@ int lbm_pipeline_solve(lbm_pipeline *p, const float *cells_in, const uint8_t *ob
 int lbm_pipeline_info(lbm_pipeline *p, int *bands, int *band_rows, int *margin_rows, double *last_ms) {
   if (!p) return fail(LBM_E_ARG, "null argument");
   if (bands) *bands = p->banded ? p->nbands : 1;
-  if (band_rows) *band_rows = p->banded ? p->band_rows : p->ny;
+  if (band_rows) *band_rows = p->banded ? p->band_rows : p->ny;  // (window pipelines are always banded)
   if (margin_rows) *margin_rows = p->banded ? p->margin : 0;
   if (last_ms) *last_ms = p->last_ms;
   return LBM_OK;

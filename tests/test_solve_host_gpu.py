@@ -76,3 +76,38 @@ def test_pipeline_is_reusable(oracle, lbm, monkeypatch):
         assert pipe.info["last_ms"] > 0
         with pytest.raises(lbm.LbmError, match="alias"):
             pipe.solve_raw(cells.ctypes.data, obst.ctypes.data, cells.ctypes.data, None)
+
+
+@pytest.mark.parametrize("nx,ny,parts,iters,band", [(256, 512, 4, 5, None),    # 128-row windows, default band sizing: 56 + 56 + 16 rows
+                                                    (256, 512, 4, 5, "32"),
+                                                    (384, 256, 2, 9, None),    # margin 15: the two windows see each other's rows twice over
+                                                    (128, 192, 3, 3, "64"),    # one band per window
+                                                    (200, 128, 1, 4, "32")])   # a single window that is the whole grid (wraps onto itself)
+def test_window_pipelines_reproduce_the_whole_grid(oracle, lbm, monkeypatch, nx, ny, parts, iters, band):
+    """lbm_pipeline_create_window: every 'rank' solves its slab from the slab's initial rows plus margin rows of its neighbours,
+    independently of the others; together they must give the single-domain oracle's lattice and av_vels."""
+    if band:
+        monkeypatch.setenv("LBM_B200_BAND_ROWS", band)
+    p, cells, obst = lbm.perturbed_problem(nx, ny, iters, seed=nx + ny + parts)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    tot, free = np.zeros(iters), 0
+    for rank in range(parts):  # rank order: the documented order of the last reduction stage
+        r0, n = rank * ny // parts, (rank + 1) * ny // parts - rank * ny // parts
+        with lbm.Pipeline(p, iters, window=(r0, n)) as pipe:
+            got, t, f = pipe.solve_window(cells, obst)
+        assert np.array_equal(got.view(np.uint32), want_cells[r0:r0 + n].view(np.uint32)), rank
+        tot, free = tot + t, free + f
+    assert free == int((obst == 0).sum())
+    av = (tot.astype(np.float32) / np.float32(free)).astype(np.float32)
+    assert ulp_distance(av, want_av).max() <= 1
+
+
+def test_window_argument_errors(lbm):
+    p = lbm.Params(256, 256, 4, 10, 0.1, 0.005, 1.85)
+    with pytest.raises(lbm.LbmError, match="multiple of 8"):
+        lbm.Pipeline(p, 4, window=(0, 100))
+    with pytest.raises(lbm.LbmError, match="not inside"):
+        lbm.Pipeline(p, 4, window=(200, 128))
+    with lbm.Pipeline(p, 4, window=(0, 128)) as pipe, pytest.raises(lbm.LbmError, match="window pipeline"):
+        pipe.solve_raw(1, 1, 2, None)
