@@ -622,8 +622,13 @@ def main():
             # and each rank's PCIe link carries both directions at once.  Checked against the sequential job above (whose
             # result is in hc) before it replaces its number; any failure on any rank keeps the sequential number.
             seq = dict(e2e)
-            ok, note, dt2, info = True, "", None, None
-            try:
+            ok, note, dt2, info, pipe, av_ulp = True, "", None, None, None, None
+            bufs = []
+
+            def everyone(flag):  # collective: did every rank get this far?  (no collective ever sits inside a try block)
+                return max_over_ranks(0.0 if flag else 1.0) == 0.0
+
+            try:  # phase 1, local: prepare the pipeline, the window buffers and one untimed warm-up job
                 pipe = lbm.Pipeline(p2, K, local_rank, window=(rows0, rows))
                 info = pipe.info
                 M = info["margin_rows"]
@@ -631,7 +636,8 @@ def main():
                 wc = lbm.host_alloc(wrows * nx * 36, local_rank)
                 wo = lbm.host_alloc(wrows * nx, local_rank)
                 out_ptr = lbm.host_alloc(nbytes_cells, local_rank)
-                if not wc or not wo or not out_ptr:
+                bufs = [q for q in (wc, wo, out_ptr) if q]
+                if len(bufs) != 3:
                     raise MemoryError("pinned host allocation failed")
                 wcells = np.ctypeslib.as_array(ctypes.cast(wc, ctypes.POINTER(ctypes.c_float)), shape=(wrows, nx, 9))
                 wobst = np.ctypeslib.as_array(ctypes.cast(wo, ctypes.POINTER(ctypes.c_uint8)), shape=(wrows, nx))
@@ -648,23 +654,32 @@ def main():
                 probe = [slice(0, 64), slice(rows // 2 - 32, rows // 2 + 32), slice(rows - 64, rows)]
                 want = [final_h[sl].copy() for sl in probe]
                 pipe.solve_window_raw(wc, wo, out_ptr)  # untimed warm-up job
+            except Exception as exc:  # noqa: BLE001 -- never lose the bench line over the optional path
+                ok, note = False, f"{type(exc).__name__}: {exc}"
+            all_ok = everyone(ok)
+            if all_ok:  # phase 2: the timed job, between barriers
+                tot2, free2 = None, 0
                 barrier()
                 t0 = time.perf_counter()
-                tot2, free2 = pipe.solve_window_raw(wc, wo, out_ptr)
+                try:
+                    tot2, free2 = pipe.solve_window_raw(wc, wo, out_ptr)
+                except Exception as exc:  # noqa: BLE001
+                    ok, note = False, f"{type(exc).__name__}: {exc}"
                 barrier()
                 dt2 = max_over_ranks(time.perf_counter() - t0)
-                pipe.close()
+                all_ok = everyone(ok)
+            if all_ok:  # phase 3: the same answer as the sequential job?
                 same = all(np.array_equal(out_h[sl].view(np.uint32), w.view(np.uint32)) for sl, w in zip(probe, want))
                 av2 = slabs.combine_av_vels(dist, tot2, free2)
                 av1 = slabs.combine_av_vels(dist, part, s2_free)
                 av_ulp = ulp_distance(av2, av1)
                 if not same or av_ulp > 1:
                     ok, note = False, f"window pipeline differs from the sequential job on rank {rank} (rows equal: {same}, av_vels ulp {av_ulp})"
-                for ptr in (wc, wo, out_ptr):
-                    lbm.lib.lbm_host_free(ptr)
-            except Exception as exc:  # noqa: BLE001 -- never lose the bench line over the optional path
-                ok, note = False, f"{type(exc).__name__}: {exc}"
-            all_ok = max_over_ranks(0.0 if ok else 1.0) == 0.0
+                all_ok = everyone(ok)
+            if pipe is not None:
+                pipe.close()
+            for ptr in bufs:
+                lbm.lib.lbm_host_free(ptr)
             if all_ok:
                 up_rows = (rows + 2 * info["margin_rows"] * info["bands"]) * world
                 e2e = {"value": round(cells * K / dt2 / 1e6, 1), "unit": "MLUPS",
