@@ -1234,6 +1234,11 @@ int lbm_run(lbm_handle *h, int iters) {
   if (iters < 0 || h->steps_done + iters > h->max_iters)
     return fail(LBM_E_ARG, "cannot run %d more steps: %d of max_iters=%d already done", iters, h->steps_done,
                 h->max_iters);
+  if (g_debug_sync && h->xghost)
+    for (const Slab &s : h->slabs)
+      if (s.stream != h->slabs[0].stream)
+        return fail(LBM_E_STATE, "LBM_B200_DEBUG_SYNC cannot be used with a block partition on several GPUs: a block launch waits for "
+                                 "its neighbours' launch of the same timestep, which a synchronisation after every launch prevents");
   const bool clustered = h->slabs.size() == 1 && h->slabs[0].cluster_ctas > 0 && iters > 0;
   const bool persistent = !clustered && h->slabs.size() == 1 && h->slabs[0].persistent_grid > 0 && iters > 0;
   // build (once) the replayable time loop before the timed region starts
