@@ -159,6 +159,8 @@ int lbm_download_fields(lbm_handle *h, float *fields);
  * CUDA graph and replayed by every later lbm_run: LBM_B200_GRAPH=0 disables, =1 forces it for any size.) */
 int lbm_save(lbm_handle *h, const char *path);
 int lbm_load(lbm_handle **out, const char *path, int num_gpus);
+/* the same onto a px x py block partition (arguments as for lbm_create_grid) */
+int lbm_load_grid(lbm_handle **out, const char *path, int px, int py, const int *devices);
 /* the problem a handle was created (or loaded) for; any pointer may be NULL */
 int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density, float *accel, float *omega);
 

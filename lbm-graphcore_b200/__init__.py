@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_host_alloc_near", "lbm_bind_thread_near", "lbm_create_rank", "lbm_ipc_blob_bytes",
-    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_problem", "lbm_create_grid", "lbm_partition", "lbm_block_info", "lbm_solve_host", "lbm_pipeline_create", "lbm_pipeline_solve",
+    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_load_grid", "lbm_problem", "lbm_create_grid", "lbm_partition", "lbm_block_info", "lbm_solve_host", "lbm_pipeline_create", "lbm_pipeline_solve",
     "lbm_pipeline_info", "lbm_pipeline_destroy", "lbm_pipeline_create_window", "lbm_pipeline_solve_window", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
 )
 
@@ -106,6 +106,7 @@ def _load() -> ctypes.CDLL:
     lib.lbm_pipeline_destroy.restype = None
     lib.lbm_save.argtypes = [c_void_p, ctypes.c_char_p]
     lib.lbm_load.argtypes = [P(c_void_p), ctypes.c_char_p, c_int]
+    lib.lbm_load_grid.argtypes = [P(c_void_p), ctypes.c_char_p, c_int, c_int, P(c_int)]
     lib.lbm_problem.argtypes = [c_void_p, P(c_int), P(c_int), P(c_int), P(c_float), P(c_float), P(c_float)]
     lib.lbm_selftest_math.argtypes = [c_int, ctypes.c_ulonglong, P(ctypes.c_ulonglong)]
     return lib
@@ -255,11 +256,16 @@ class Solver:
         self.row_begin, self.row_count = rb.value, rc.value
 
     @classmethod
-    def load(cls, path: str, num_gpus: int = 1, reynolds_dim: int = 10) -> "Solver":
-        """lbm_load: a solver restored from a file written by save() (the reference's --exe)."""
+    def load(cls, path: str, num_gpus: int = 1, reynolds_dim: int = 10, grid: tuple[int, int] | None = None,
+             devices: list[int] | None = None) -> "Solver":
+        """lbm_load / lbm_load_grid: a solver restored from a file written by save() (the reference's --exe)."""
         self = cls.__new__(cls)
         self._h = ctypes.c_void_p()
-        _check(lib.lbm_load(ctypes.byref(self._h), os.fsencode(path), num_gpus))
+        if grid is not None:
+            arr = (ctypes.c_int * (grid[0] * grid[1]))(*devices) if devices is not None else None
+            _check(lib.lbm_load_grid(ctypes.byref(self._h), os.fsencode(path), grid[0], grid[1], arr))
+        else:
+            _check(lib.lbm_load(ctypes.byref(self._h), os.fsencode(path), num_gpus))
         nx, ny, it = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         d, a, o = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
         _check(lib.lbm_problem(self._h, ctypes.byref(nx), ctypes.byref(ny), ctypes.byref(it), ctypes.byref(d),

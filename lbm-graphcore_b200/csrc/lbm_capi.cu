@@ -1497,7 +1497,10 @@ int lbm_save(lbm_handle *h, const char *path) {
   return LBM_OK;
 }
 
-int lbm_load(lbm_handle **out, const char *path, int num_gpus) {
+}  // extern "C"
+namespace {
+// px == 0: row slabs on num_gpus GPUs (lbm_create); otherwise px x py blocks (lbm_create_grid)
+int load_solver(lbm_handle **out, const char *path, int num_gpus, int px, int py, const int *devices) {
   if (!out || !path) return fail(LBM_E_ARG, "null argument");
   *out = nullptr;
   FileCloser fc{fopen(path, "rb")};
@@ -1509,7 +1512,8 @@ int lbm_load(lbm_handle **out, const char *path, int num_gpus) {
     return fail(LBM_E_ARG, "%s has version %u (this library reads version 1)", path, hd.version);
   if (hd.steps_done < 0 || hd.steps_done > hd.max_iters) return fail(LBM_E_ARG, "%s: corrupt step counter", path);
   lbm_handle *h = nullptr;
-  int rc = lbm_create(&h, hd.nx, hd.ny, hd.max_iters, hd.density, hd.accel, hd.omega, num_gpus);
+  int rc = px > 0 ? lbm_create_grid(&h, hd.nx, hd.ny, hd.max_iters, hd.density, hd.accel, hd.omega, px, py, devices)
+                  : lbm_create(&h, hd.nx, hd.ny, hd.max_iters, hd.density, hd.accel, hd.omega, num_gpus);
   if (rc) return rc;
   auto bail = [&](int code) { lbm_destroy(h); return code; };
   rc = reset_counters(h);
@@ -1548,6 +1552,15 @@ int lbm_load(lbm_handle **out, const char *path, int num_gpus) {
   for (Slab &s : h->slabs) s.window_first = hd.steps_done;
   *out = h;
   return LBM_OK;
+}
+}  // namespace
+extern "C" {
+
+int lbm_load(lbm_handle **out, const char *path, int num_gpus) { return load_solver(out, path, num_gpus, 0, 0, nullptr); }
+
+int lbm_load_grid(lbm_handle **out, const char *path, int px, int py, const int *devices) {
+  if (px < 1 || py < 1) return fail(LBM_E_ARG, "the block grid must be at least 1 x 1 (got %d x %d)", px, py);
+  return load_solver(out, path, 0, px, py, devices);
 }
 
 int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density, float *accel, float *omega) {

@@ -272,7 +272,9 @@ int main(int argc, char *argv[]) {
   int rc = LBM_OK;
   int steps_before = 0;
   if (have_exe) {
-    timedStep("Loading prepared solver to device", [&]() { rc = lbm_load(&engine, opt.exe.c_str(), opt.num_gpus); });
+    timedStep("Loading prepared solver to device", [&]() {
+      rc = grid_px > 0 ? lbm_load_grid(&engine, opt.exe.c_str(), grid_px, grid_py, nullptr) : lbm_load(&engine, opt.exe.c_str(), opt.num_gpus);
+    });
     if (rc != LBM_OK) return die("lbm_load");
     int nx = 0, ny = 0, max_iters = 0;
     float density = 0, accel = 0, omega = 0;

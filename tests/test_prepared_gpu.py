@@ -120,3 +120,26 @@ def test_runner_prepare_then_exe_and_resume(lbm, tmp_path):
     r = subprocess.run([lbm.RUNNER_PATH, "--params", params_path("128x128"), "--obstacles", obstacles_path("128x128"), "--exe", exe,
                         "--outdir", str(rest), "--reruns", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "different problem" in r.stderr
+
+
+def test_save_from_slabs_load_onto_blocks_and_back(oracle, lbm, tmp_path):
+    """The file holds host interchange formats, so a state saved from three row slabs continues on a 2 x 2 block partition
+    (lbm_load_grid) and a state saved from blocks continues on one slab -- all bit-exact."""
+    nx, ny, iters = 384, 96, 45
+    p, cells, obst = lbm.perturbed_problem(nx, ny, iters, seed=321)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    a, b = str(tmp_path / "a.lbm"), str(tmp_path / "b.lbm")
+    with lbm.Solver(p, devices=[0, 0, 0]) as s:
+        s.upload(cells, obst)
+        s.run(14)
+        s.save(a)
+    with lbm.Solver.load(a, grid=(2, 2), devices=[0, 0, 0, 0]) as s:
+        assert s.partition == (2, 2) and s.steps_done == 14
+        s.run(17)
+        s.save(b)
+    with lbm.Solver.load(b) as s:
+        s.run(iters - 31)
+        got_cells, got_av = s.download()
+    assert np.array_equal(_bits(got_cells), _bits(want_cells))
+    assert ulp_distance(got_av, want_av).max() <= 1
