@@ -77,3 +77,20 @@ def test_our_arm_line_on_a_gpu():
     base = j["cpu_baseline"]
     assert base["kind"] == "port" and base["cores"] >= 1 and base["value"] > 0
     assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+@pytest.mark.gpu
+def test_partition_comparison_mode_on_one_gpu():
+    """bench.py --in-process N [--grid PXxPY] (the row-slab vs block comparison runs of DESIGN 5.2), here with one GPU: a 1 x 1 block
+    "grid" whose ghost columns wrap onto the block itself, against the plain single slab."""
+    out = {}
+    for extra in ([], ["--grid", "1x1"]):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--in-process", "1", "--nx", "2048", "--ny", "1024", "--steps", "20",
+                            "--warmup", "3", *extra], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        assert j["n_gpus"] == 1 and j["e2e"] is None and "parity" not in j and "shipped" not in j
+        out[bool(extra)] = j
+    assert "blocks with ghost columns" in out[True]["detail"]["partition"] and "row slabs" in out[False]["detail"]["partition"]
+    assert out[True]["detail"]["av_vels_last"] == pytest.approx(out[False]["detail"]["av_vels_last"], rel=1e-6)
+    assert out[True]["roofline"]["kernel"].endswith(",true>") and out[False]["roofline"]["kernel"].endswith(",false>")
