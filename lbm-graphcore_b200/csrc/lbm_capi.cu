@@ -8,6 +8,7 @@
 #include "lbm_partition.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cstdarg>
 #include <cstdio>
@@ -1455,7 +1456,9 @@ struct FileCloser {
 };
 }  // namespace
 
-int lbm_save(lbm_handle *h, const char *path) {
+}  // extern "C"
+namespace {
+int save_solver(lbm_handle *h, const char *path) {
   if (!h || !path) return fail(LBM_E_ARG, "null argument");
   if (!h->uploaded) return fail(LBM_E_STATE, "lbm_save before lbm_upload");
   if (h->rank_mode && h->world > 1)
@@ -1497,8 +1500,6 @@ int lbm_save(lbm_handle *h, const char *path) {
   return LBM_OK;
 }
 
-}  // extern "C"
-namespace {
 // px == 0: row slabs on num_gpus GPUs (lbm_create); otherwise px x py blocks (lbm_create_grid)
 int load_solver(lbm_handle **out, const char *path, int num_gpus, int px, int py, const int *devices) {
   if (!out || !path) return fail(LBM_E_ARG, "null argument");
@@ -1511,6 +1512,14 @@ int load_solver(lbm_handle **out, const char *path, int num_gpus, int px, int py
   if (hd.version != 1 || hd.header_bytes != sizeof hd)
     return fail(LBM_E_ARG, "%s has version %u (this library reads version 1)", path, hd.version);
   if (hd.steps_done < 0 || hd.steps_done > hd.max_iters) return fail(LBM_E_ARG, "%s: corrupt step counter", path);
+  if (hd.nx < 1 || hd.ny < 1) return fail(LBM_E_ARG, "%s: corrupt grid size", path);
+  // host buffers first (they may throw; nothing to undo yet).  The obstacle bytes come first in the file but upload_rows wants
+  // both: the obstacles are read whole (1 B per cell), the cells chunk by chunk
+  const size_t row_bytes = (size_t)hd.nx * lbm::kSpeeds * sizeof(float);
+  const int rows_per_chunk = (int)std::max<size_t>(1, kSaveChunkBytes / row_bytes);
+  std::vector<uint8_t> obst((size_t)hd.nx * hd.ny);
+  std::vector<char> buf((size_t)std::min(rows_per_chunk, hd.ny) * row_bytes);
+  std::vector<double> tot((size_t)std::max(hd.steps_done, 1));
   lbm_handle *h = nullptr;
   int rc = px > 0 ? lbm_create_grid(&h, hd.nx, hd.ny, hd.max_iters, hd.density, hd.accel, hd.omega, px, py, devices)
                   : lbm_create(&h, hd.nx, hd.ny, hd.max_iters, hd.density, hd.accel, hd.omega, num_gpus);
@@ -1518,13 +1527,7 @@ int load_solver(lbm_handle **out, const char *path, int num_gpus, int px, int py
   auto bail = [&](int code) { lbm_destroy(h); return code; };
   rc = reset_counters(h);
   if (rc) return bail(rc);
-  const size_t row_bytes = (size_t)h->nx * lbm::kSpeeds * sizeof(float);
-  const int rows_per_chunk = (int)std::max<size_t>(1, kSaveChunkBytes / row_bytes);
-  // the obstacle bytes come first in the file but upload_rows wants both: read the obstacles whole (1 B per cell),
-  // the cells chunk by chunk
-  std::vector<uint8_t> obst((size_t)hd.nx * hd.ny);
   if (fread(obst.data(), 1, obst.size(), fc.f) != obst.size()) return bail(fail(LBM_E_ARG, "%s is truncated (obstacles)", path));
-  std::vector<char> buf((size_t)std::min(rows_per_chunk, h->ny) * row_bytes);
   for (int r = 0; r < h->ny; r += rows_per_chunk) {
     const int n = std::min(rows_per_chunk, h->ny - r);
     if (fread(buf.data(), row_bytes, (size_t)n, fc.f) != (size_t)n) return bail(fail(LBM_E_ARG, "%s is truncated (cells)", path));
@@ -1542,11 +1545,11 @@ int load_solver(lbm_handle **out, const char *path, int num_gpus, int px, int py
   h->steps_done = hd.steps_done;
   h->first_run_pending = hd.first_run_pending != 0;
   if (hd.steps_done) {
-    std::vector<double> tot((size_t)hd.steps_done);
-    if (fread(tot.data(), sizeof(double), tot.size(), fc.f) != tot.size()) return bail(fail(LBM_E_ARG, "%s is truncated (tot_u)", path));
+    if (fread(tot.data(), sizeof(double), (size_t)hd.steps_done, fc.f) != (size_t)hd.steps_done)
+      return bail(fail(LBM_E_ARG, "%s is truncated (tot_u)", path));
     Slab &s0 = h->slabs[0];
     cudaError_t e = cudaSetDevice(s0.device);
-    if (e == cudaSuccess) e = cudaMemcpy(s0.tot_u, tot.data(), tot.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s0.tot_u, tot.data(), (size_t)hd.steps_done * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(LBM_E_CUDA, "restoring tot_u: %s", cudaGetErrorString(e)));
   }
   for (Slab &s : h->slabs) s.window_first = hd.steps_done;
@@ -1556,11 +1559,30 @@ int load_solver(lbm_handle **out, const char *path, int num_gpus, int px, int py
 }  // namespace
 extern "C" {
 
-int lbm_load(lbm_handle **out, const char *path, int num_gpus) { return load_solver(out, path, num_gpus, 0, 0, nullptr); }
+// (the staging buffers of save / load are hundreds of MB: an allocation failure must come back as a code, not as an exception)
+int lbm_save(lbm_handle *h, const char *path) {
+  try {
+    return save_solver(h, path);
+  } catch (const std::exception &e) {
+    return fail(LBM_E_NOMEM, "lbm_save: %s", e.what());
+  }
+}
+
+int lbm_load(lbm_handle **out, const char *path, int num_gpus) {
+  try {
+    return load_solver(out, path, num_gpus, 0, 0, nullptr);
+  } catch (const std::exception &e) {
+    return fail(LBM_E_NOMEM, "lbm_load: %s", e.what());
+  }
+}
 
 int lbm_load_grid(lbm_handle **out, const char *path, int px, int py, const int *devices) {
   if (px < 1 || py < 1) return fail(LBM_E_ARG, "the block grid must be at least 1 x 1 (got %d x %d)", px, py);
-  return load_solver(out, path, 0, px, py, devices);
+  try {
+    return load_solver(out, path, 0, px, py, devices);
+  } catch (const std::exception &e) {
+    return fail(LBM_E_NOMEM, "lbm_load_grid: %s", e.what());
+  }
 }
 
 int lbm_problem(lbm_handle *h, int *nx, int *ny, int *max_iters, float *density, float *accel, float *omega) {
@@ -1748,16 +1770,32 @@ int pipeline_run(lbm_pipeline *p, const float *cells_in, const uint8_t *obstacle
   std::vector<int> codes(p->workers, LBM_OK);
   std::vector<std::string> messages(p->workers);
   std::vector<std::thread> threads;
-  for (int w = 0; w < p->workers; ++w)
-    threads.emplace_back([&, w]() {
-      for (int b = w; b < p->nbands && codes[w] == LBM_OK; b += p->workers) {
-        const int rows = std::min(p->band_rows, p->rows - b * p->band_rows);
-        lbm_handle *h = rows == p->band_rows ? p->full[w] : p->last[w];
-        const int r = solve_band(p, h, job, b);
-        if (r != LBM_OK) { codes[w] = r; messages[w] = g_last_error; }
-      }
-    });
-  for (std::thread &t : threads) t.join();
+  threads.reserve(p->workers);
+  std::atomic<bool> stop{false};  // a worker failed, or a thread could not be started: the others finish their band and leave
+  bool spawned = true;
+  for (int w = 0; w < p->workers && spawned; ++w) {
+    try {
+      threads.emplace_back([&, w]() {
+        try {
+          for (int b = w; b < p->nbands && !stop.load(); b += p->workers) {
+            const int rows = std::min(p->band_rows, p->rows - b * p->band_rows);
+            lbm_handle *h = rows == p->band_rows ? p->full[w] : p->last[w];
+            const int r = solve_band(p, h, job, b);
+            if (r != LBM_OK) { codes[w] = r; messages[w] = g_last_error; stop.store(true); }
+          }
+        } catch (const std::exception &e) {  // nothing may escape a worker thread (it would terminate the process)
+          codes[w] = LBM_E_NOMEM;
+          messages[w] = e.what();
+          stop.store(true);
+        }
+      });
+    } catch (const std::exception &) {  // no more threads: stop the ones that run, then report
+      spawned = false;
+      stop.store(true);
+    }
+  }
+  for (std::thread &t : threads) t.join();  // always, before anything can unwind past the vector of joinable threads
+  if (!spawned) return fail(LBM_E_NOMEM, "could not start the pipeline's worker threads");
   for (int w = 0; w < p->workers; ++w)
     if (codes[w] != LBM_OK) return fail(codes[w], "band solver: %s", messages[w].c_str());
   free_cells = 0;
