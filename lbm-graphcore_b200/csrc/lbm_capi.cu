@@ -59,7 +59,8 @@ const bool g_debug_sync = getenv("LBM_B200_DEBUG_SYNC") != nullptr;
   } while (0)
 
 constexpr size_t kFlagBytes = 256;        // exported flag area at the end of a slab's allocation (south, north, six sides)
-constexpr size_t kStageBytes = 64u << 20;  // AoS staging chunk for upload/download
+// AoS staging buffer for upload/download, used as two halves (LBM_B200_STAGE_MB overrides the size: tuning runs)
+const size_t kStageBytes = (size_t)(getenv("LBM_B200_STAGE_MB") ? std::max(8, atoi(getenv("LBM_B200_STAGE_MB"))) : 64) << 20;
 constexpr int kClusterChunkSteps = 8192;  // timesteps per launch of the cluster-resident kernel
 constexpr int kPersistentMaxCtas = 1024;  // upper bound on the persistent kernel's grid
 constexpr size_t kPersistentPartials = 2 * (size_t)kPersistentMaxCtas * lbm::kTileH;
@@ -551,7 +552,7 @@ int launch_cluster(lbm_handle *h, Slab &s, int iters) {
 // ---- staged host <-> device pipelines -------------------------------------------------------------
 // Rows travel in chunks through the two halves of the slab's staging buffer.  `chunk` counts chunks since the last
 // drain so that consecutive pipelines (cells, then obstacles) keep alternating halves correctly.
-constexpr size_t kHalfStage = kStageBytes / 2;
+const size_t kHalfStage = kStageBytes / 2;
 
 // host -> staging half (copy_stream) -> `consume(stage_half, first_row, rows)` launches a kernel on s.stream
 // (host rows are `host_pitch` bytes apart: the rows of a 2-D block are pieces of the caller's full-width rows)
