@@ -63,3 +63,37 @@ def test_halo_plan_reproduces_single_domain_run_over_gloo(world, nx, ny, iters):
         outs.append(out)
     assert all(pr.returncode == 0 for pr in procs), "\n".join(o[-3000:] for o in outs)
     assert "gloo slab model ok" in outs[0]
+
+
+def test_two_phase_teardown_order_over_gloo(tmp_path):
+    """slabs.close_ring (the protocol of include/lbm_b200.h): no rank drops its mappings while another may still be running,
+    and no rank frees its slab while another still has it mapped -- whatever the skew between the ranks."""
+    import json
+    world, port = 3, _free_port()
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "teardown_gloo_worker.py"), str(tmp_path)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for pr in procs:
+        out, _ = pr.communicate(timeout=120)
+        assert pr.returncode == 0, out[-2000:]
+    ev = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(world)]
+    assert max(e["still_running_until"] for e in ev) <= min(e["disconnect"] for e in ev)
+    assert max(e["disconnect"] for e in ev) <= min(e["close"] for e in ev)
+
+
+def test_close_ring_without_a_group_just_closes():
+    class S:
+        closed = False
+
+        def close(self):
+            self.closed = True
+
+        def ipc_disconnect(self):
+            raise AssertionError("a single-process solver has nothing to disconnect")
+
+    s = S()
+    slabs.close_ring(s, None)
+    assert s.closed
