@@ -188,6 +188,9 @@ int lbm_pipeline_create_window(lbm_pipeline **out, int nx, int ny, int row_begin
                                float accel, float omega, int device);
 int lbm_pipeline_solve_window(lbm_pipeline *p, const float *cells_window, const uint8_t *obstacles_window, float *cells_out,
                               double *tot_u, long long *free_cells);
+/* how a job WOULD be cut, without creating anything (no GPU needed): window_rows = 0 for the whole grid, else one rank's
+ * row count.  bands = 1 and margin_rows = 0 mean "not banded". */
+int lbm_pipeline_plan(int nx, int ny, int window_rows, int iters, int *bands, int *band_rows, int *margin_rows);
 /* how the job is cut (1 band = not banded) and the wall time of the last solve; any pointer may be NULL */
 int lbm_pipeline_info(lbm_pipeline *p, int *bands, int *band_rows, int *margin_rows, double *last_ms);
 void lbm_pipeline_destroy(lbm_pipeline *p);

@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_host_alloc_near", "lbm_bind_thread_near", "lbm_create_rank", "lbm_ipc_blob_bytes",
     "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_load_grid", "lbm_problem", "lbm_create_grid", "lbm_partition", "lbm_block_info", "lbm_solve_host", "lbm_pipeline_create", "lbm_pipeline_solve",
-    "lbm_pipeline_info", "lbm_pipeline_destroy", "lbm_pipeline_create_window", "lbm_pipeline_solve_window", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
+    "lbm_pipeline_info", "lbm_pipeline_destroy", "lbm_pipeline_create_window", "lbm_pipeline_solve_window", "lbm_pipeline_plan", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
 )
 
 
@@ -102,6 +102,7 @@ def _load() -> ctypes.CDLL:
     lib.lbm_pipeline_create_window.argtypes = [P(c_void_p), c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int]
     lib.lbm_pipeline_solve_window.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(ctypes.c_longlong)]
     lib.lbm_pipeline_info.argtypes = [c_void_p, P(c_int), P(c_int), P(c_int), P(ctypes.c_double)]
+    lib.lbm_pipeline_plan.argtypes = [c_int, c_int, c_int, c_int, P(c_int), P(c_int), P(c_int)]
     lib.lbm_pipeline_destroy.argtypes = [c_void_p]
     lib.lbm_pipeline_destroy.restype = None
     lib.lbm_save.argtypes = [c_void_p, ctypes.c_char_p]
@@ -131,6 +132,13 @@ def selftest_math(device: int = 0, pairs: int = 1 << 32) -> dict:
 def host_alloc(nbytes: int, device: int | None = None) -> int:
     """Pinned host memory (address, or 0/None on failure); near GPU `device`'s NUMA node when given. Free with lib.lbm_host_free."""
     return lib.lbm_host_alloc(nbytes) if device is None else lib.lbm_host_alloc_near(nbytes, device)
+
+
+def pipeline_plan(nx: int, ny: int, iters: int, window_rows: int = 0) -> dict:
+    """lbm_pipeline_plan: how a job would be cut into bands (needs no GPU)."""
+    b, r, m = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _check(lib.lbm_pipeline_plan(nx, ny, window_rows, iters, ctypes.byref(b), ctypes.byref(r), ctypes.byref(m)))
+    return {"bands": b.value, "band_rows": r.value, "margin_rows": m.value}
 
 
 class Pipeline:

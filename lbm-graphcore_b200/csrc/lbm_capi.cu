@@ -1705,6 +1705,20 @@ void lbm_pipeline_destroy(lbm_pipeline *p) {
 }  // extern "C"
 namespace {
 
+// How a job of `iters` timesteps on `rows` rows (the whole grid, or one rank's window of it) is cut into bands.
+void plan_bands(int nx, int ny, bool window, int rows, int iters, bool &banded, int &band_rows, int &margin) {
+  // the margin: >= iters rows, and M + 1 a multiple of the tile height so that a band is whole tile rows of its solver
+  margin = ((std::max(iters, 1) + 1 + lbm::kTileH - 1) / lbm::kTileH) * lbm::kTileH - 1;
+  const int min_band = (8 * margin + lbm::kTileH - 1) / lbm::kTileH * lbm::kTileH;  // margins at most a quarter of the upload
+  long long want = std::max<long long>(lbm::kTileH, kSolveBandCells / nx / lbm::kTileH * lbm::kTileH);
+  if (window) want = std::min<long long>(want, std::max(lbm::kTileH, rows / 4 / lbm::kTileH * lbm::kTileH));  // a slab: at least four bands
+  band_rows = (int)want;
+  if (const char *e = getenv("LBM_B200_BAND_ROWS")) band_rows = std::max(lbm::kTileH, atoi(e) / lbm::kTileH * lbm::kTileH);  // tests
+  else if (window) band_rows = std::min(rows, std::max(band_rows, min_band));
+  // bands pay when the margins are a small part of a band and there are enough bands to overlap; a window has no other way
+  banded = window || (ny % lbm::kTileH == 0 && band_rows >= min_band && ny >= 4 * band_rows && !getenv("LBM_B200_NO_BANDS"));
+}
+
 // window == false: the whole grid (row0 = 0, rows = ny)
 int pipeline_create(lbm_pipeline **out, int nx, int ny, bool window, int row0, int rows, int iters, float density, float accel,
                     float omega, int device) {
@@ -1719,16 +1733,7 @@ int pipeline_create(lbm_pipeline **out, int nx, int ny, bool window, int row0, i
   p->nx = nx; p->ny = ny; p->iters = iters; p->device = device;
   p->density = density; p->accel = accel; p->omega = omega;
   p->window = window; p->row0 = row0; p->rows = rows;
-  // the margin: >= iters rows, and M + 1 a multiple of the tile height so that a band is whole tile rows of its solver
-  p->margin = ((std::max(iters, 1) + 1 + lbm::kTileH - 1) / lbm::kTileH) * lbm::kTileH - 1;
-  const int min_band = (8 * p->margin + lbm::kTileH - 1) / lbm::kTileH * lbm::kTileH;  // margins at most a quarter of the upload
-  long long want = std::max<long long>(lbm::kTileH, kSolveBandCells / nx / lbm::kTileH * lbm::kTileH);
-  if (window) want = std::min<long long>(want, std::max(lbm::kTileH, rows / 4 / lbm::kTileH * lbm::kTileH));  // a slab: at least four bands
-  p->band_rows = (int)want;
-  if (const char *e = getenv("LBM_B200_BAND_ROWS")) p->band_rows = std::max(lbm::kTileH, atoi(e) / lbm::kTileH * lbm::kTileH);  // tests
-  else if (window) p->band_rows = std::min(rows, std::max(p->band_rows, min_band));
-  // bands pay when the margins are a small part of a band and there are enough bands to overlap; a window has no other way
-  p->banded = window || (ny % lbm::kTileH == 0 && p->band_rows >= min_band && ny >= 4 * p->band_rows && !getenv("LBM_B200_NO_BANDS"));
+  plan_bands(nx, ny, window, rows, iters, p->banded, p->band_rows, p->margin);
   if (!p->banded) {
     rc = lbm_create_on_devices(&p->whole, nx, ny, iters, density, accel, omega, 1, &device);
     if (rc) { lbm_pipeline_destroy(p); return rc; }
@@ -1863,6 +1868,21 @@ int lbm_pipeline_solve_window(lbm_pipeline *p, const float *cells_window, const 
     return fail(LBM_E_NOMEM, "lbm_pipeline_solve_window: %s", e.what());
   }
   p->last_ms = now_ms() - t_begin;
+  return LBM_OK;
+}
+
+int lbm_pipeline_plan(int nx, int ny, int window_rows, int iters, int *bands, int *band_rows, int *margin_rows) {
+  const bool window = window_rows > 0;
+  const int rows = window ? window_rows : ny;
+  int rc = check_problem(nx, ny, iters, 1);
+  if (rc) return rc;
+  if (window && (rows > ny || rows % lbm::kTileH != 0)) return fail(LBM_E_ARG, "a window must be a multiple of %d rows inside the grid", lbm::kTileH);
+  bool banded = false;
+  int band = 0, margin = 0;
+  plan_bands(nx, ny, window, rows, iters, banded, band, margin);
+  if (bands) *bands = banded ? (rows + band - 1) / band : 1;
+  if (band_rows) *band_rows = banded ? band : ny;
+  if (margin_rows) *margin_rows = banded ? margin : 0;
   return LBM_OK;
 }
 

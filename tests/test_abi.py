@@ -189,3 +189,26 @@ def test_new_entry_points_validate_before_touching_cuda(lbm, tmp_path):
         assert lbm.lib.lbm_create_grid(ctypes.byref(h), 64, 64, 1, 0.1, 0.005, 1.85, 1, 1, None) == -2
         assert lbm.lib.lbm_pipeline_create(ctypes.byref(p), 64, 64, 1, 0.1, 0.005, 1.85, 0) == -2
         assert b"CUDA" in lbm.lib.lbm_last_error() or b"device" in lbm.lib.lbm_last_error()
+
+
+def test_pipeline_plan_without_a_gpu(lbm, monkeypatch):
+    """lbm_pipeline_plan: the band cut of a whole job / of one rank's window.  The margin covers the steps and ends on a tile
+    row; bands are whole tile rows and at least 8 margins tall; jobs too long or grids too small are not banded."""
+    monkeypatch.delenv("LBM_B200_BAND_ROWS", raising=False)
+    monkeypatch.delenv("LBM_B200_NO_BANDS", raising=False)
+    assert lbm.pipeline_plan(16384, 16384, 20) == {"bands": 16, "band_rows": 1024, "margin_rows": 23}
+    assert lbm.pipeline_plan(16384, 16384, 200) == {"bands": 1, "band_rows": 16384, "margin_rows": 0}  # 8 x 207 rows > a band
+    assert lbm.pipeline_plan(2048, 2048, 20)["bands"] == 1                                            # fewer than four bands
+    for nx, ny, iters in ((16384, 16384, 1), (16384, 16384, 7), (8192, 32768, 50), (32768, 32768, 20)):
+        plan = lbm.pipeline_plan(nx, ny, iters)
+        if plan["bands"] > 1:
+            m, b = plan["margin_rows"], plan["band_rows"]
+            assert m >= iters and (m + 1) % 8 == 0 and b % 8 == 0 and b >= 8 * m and plan["bands"] == -(-ny // b) >= 4
+    # one rank's slab of the 16384^2 grid on 2 / 4 / 8 GPUs: always banded, at least four bands where the margins allow
+    assert lbm.pipeline_plan(16384, 16384, 20, window_rows=8192) == {"bands": 8, "band_rows": 1024, "margin_rows": 23}
+    assert lbm.pipeline_plan(16384, 16384, 20, window_rows=4096) == {"bands": 4, "band_rows": 1024, "margin_rows": 23}
+    assert lbm.pipeline_plan(16384, 16384, 20, window_rows=2048) == {"bands": 4, "band_rows": 512, "margin_rows": 23}
+    assert lbm.pipeline_plan(16384, 16384, 100, window_rows=2048) == {"bands": 3, "band_rows": 824, "margin_rows": 103}
+    assert lbm.pipeline_plan(256, 256, 300, window_rows=128)["bands"] == 1  # a window is one band when nothing else fits
+    with pytest.raises(lbm.LbmError, match="multiple of 8"):
+        lbm.pipeline_plan(256, 256, 3, window_rows=100)
