@@ -234,6 +234,11 @@ int lbm_bind_thread_near(int device);
 
 int lbm_create_rank(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel,
                     float omega, int rank, int world, int device);
+/* the same for a px x py BLOCK partition (lbm_create_grid's layout, one rank per block; rank = by * px + bx): up to eight
+ * neighbouring ranks are mapped by lbm_ipc_connect.  lbm_upload / lbm_download / lbm_download_fields then take / return only
+ * the rank's block, row_count rows of col_count cells (lbm_block_info(h, 0, ...)). */
+int lbm_create_rank_grid(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel, float omega, int rank,
+                         int px, int py, int device);
 size_t lbm_ipc_blob_bytes(void);
 int lbm_ipc_export(lbm_handle *h, void *blob);
 /* blobs: world * lbm_ipc_blob_bytes() bytes, rank-major */

@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_steps_done", "lbm_free_cells",
     "lbm_launch_count", "lbm_kernel_variant", "lbm_create_on_devices", "lbm_init_synthetic", "lbm_rows",
     "lbm_download_tot_u", "lbm_host_alloc", "lbm_host_free", "lbm_host_alloc_near", "lbm_bind_thread_near", "lbm_create_rank", "lbm_ipc_blob_bytes",
-    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_load_grid", "lbm_problem", "lbm_create_grid", "lbm_partition", "lbm_block_info", "lbm_solve_host", "lbm_pipeline_create", "lbm_pipeline_solve",
+    "lbm_ipc_export", "lbm_ipc_connect", "lbm_ipc_disconnect", "lbm_save", "lbm_load", "lbm_load_grid", "lbm_problem", "lbm_create_grid", "lbm_create_rank_grid", "lbm_partition", "lbm_block_info", "lbm_solve_host", "lbm_pipeline_create", "lbm_pipeline_solve",
     "lbm_pipeline_info", "lbm_pipeline_destroy", "lbm_pipeline_create_window", "lbm_pipeline_solve_window", "lbm_pipeline_plan", "lbm_selftest_math", "lbm_download_fields", "lbm_slab_count", "lbm_slab_info",
 )
 
@@ -93,6 +93,7 @@ def _load() -> ctypes.CDLL:
     lib.lbm_ipc_connect.argtypes = [c_void_p, c_void_p]
     lib.lbm_ipc_disconnect.argtypes = [c_void_p]
     lib.lbm_create_grid.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_int, P(c_int)]
+    lib.lbm_create_rank_grid.argtypes = [P(c_void_p), c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_int, c_int]
     lib.lbm_partition.argtypes = [c_void_p, P(c_int), P(c_int)]
     lib.lbm_block_info.argtypes = [c_void_p, c_int, P(c_int), P(c_int), P(c_int), P(c_int), P(c_int), P(ctypes.c_longlong)]
     lib.lbm_solve_host.argtypes = [c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -248,7 +249,9 @@ class Solver:
         self._h = ctypes.c_void_p()
         p = params
         args = (p.nx, p.ny, p.max_iters, p.density, p.accel, p.omega)
-        if grid is not None:  # (px, py) blocks; devices = GPU of block by * px + bx (default: one GPU each)
+        if grid is not None and rank is not None:  # one process per GPU, this rank owns block `rank` of the px x py grid
+            _check(lib.lbm_create_rank_grid(ctypes.byref(self._h), *args, rank, grid[0], grid[1], device))
+        elif grid is not None:  # (px, py) blocks; devices = GPU of block by * px + bx (default: one GPU each)
             px, py = grid
             arr = (ctypes.c_int * (px * py))(*devices) if devices is not None else None
             _check(lib.lbm_create_grid(ctypes.byref(self._h), *args, px, py, arr))
@@ -262,6 +265,11 @@ class Solver:
         rb, rc = ctypes.c_int(), ctypes.c_int()
         _check(lib.lbm_rows(self._h, ctypes.byref(rb), ctypes.byref(rc)))
         self.row_begin, self.row_count = rb.value, rc.value
+        # the columns a caller passes per row: all of them, except for a rank that owns one block of a block partition
+        self.col_begin, self.col_count = 0, p.nx
+        if grid is not None and rank is not None:
+            b = self.blocks[0]
+            self.col_begin, self.col_count = b["col_begin"], b["col_count"]
 
     @classmethod
     def load(cls, path: str, num_gpus: int = 1, reynolds_dim: int = 10, grid: tuple[int, int] | None = None,
@@ -280,6 +288,7 @@ class Solver:
                                ctypes.byref(a), ctypes.byref(o)))
         self.params = Params(nx.value, ny.value, it.value, reynolds_dim, d.value, a.value, o.value)
         self.row_begin, self.row_count = 0, ny.value
+        self.col_begin, self.col_count = 0, nx.value
         return self
 
     def save(self, path: str) -> None:
@@ -311,8 +320,8 @@ class Solver:
         p = self.params
         cells = np.ascontiguousarray(cells, dtype=np.float32)
         obstacles = np.ascontiguousarray(obstacles).astype(np.uint8, copy=False)
-        if cells.size != self.row_count * p.nx * NSPEEDS or obstacles.size != self.row_count * p.nx:
-            raise ValueError("cells/obstacles do not match the rows owned by this solver")
+        if cells.size != self.row_count * self.col_count * NSPEEDS or obstacles.size != self.row_count * self.col_count:
+            raise ValueError("cells/obstacles do not match the rows (and columns) owned by this solver")
         _check(lib.lbm_upload(self._h, cells.ctypes.data, obstacles.ctypes.data))
 
     def upload_raw(self, cells_ptr: int, obstacles_ptr: int) -> None:
@@ -328,7 +337,7 @@ class Solver:
     def download(self, cells: bool = True, av_vels: bool = True):
         """engine.run(2): returns (cells float32[rows, nx, 9] | None, av_vels float32[steps] | None)."""
         p = self.params
-        c = np.empty((self.row_count, p.nx, NSPEEDS), dtype=np.float32) if cells else None
+        c = np.empty((self.row_count, self.col_count, NSPEEDS), dtype=np.float32) if cells else None
         a = np.zeros(max(p.max_iters, 1), dtype=np.float32) if av_vels else None
         _check(lib.lbm_download(self._h, c.ctypes.data if cells else None, a.ctypes.data if av_vels else None))
         return c, (a[: self.steps_done] if av_vels else None)
@@ -338,7 +347,7 @@ class Solver:
 
     def download_fields(self) -> np.ndarray:
         """u_x, u_y, u, pressure per cell, computed on the device: float32[rows, nx, 4]."""
-        f = np.empty((self.row_count, self.params.nx, 4), dtype=np.float32)
+        f = np.empty((self.row_count, self.col_count, 4), dtype=np.float32)
         _check(lib.lbm_download_fields(self._h, f.ctypes.data))
         return f
 

@@ -150,6 +150,8 @@ struct lbm_handle {
   bool xghost = false;     // 2-D block partition: blocks keep ghost columns (lbm_create_grid)
   int px = 1, py = 1;      // blocks per row / per column of the partition (1 x slabs for row slabs)
   bool rank_mode = false;  // one process per GPU
+  // a rank of a block partition passes / receives only its block: host rows are nxl cells wide and start at its first column
+  bool rank_block() const { return rank_mode && xghost; }
   int rank = 0, world = 1;
   bool connected = false;
   std::vector<void *> ipc_opened;
@@ -893,6 +895,106 @@ int lbm_create_rank(lbm_handle **out, int nx, int ny, int max_iters, float densi
   return LBM_OK;
 }
 
+}  // extern "C"
+namespace {
+// one process per GPU, block partition: map the (up to eight distinct) neighbouring ranks' allocations and point this
+// block's halo stores and flags at them.  A neighbour that is this rank itself (px or py of 1 or 2 make that common) needs
+// no mapping.
+int connect_block_neighbours(lbm_handle *h, const char *all) {
+  Slab &s = h->slabs[0];
+  const int px = h->px, py = h->py, bx = h->rank % px, by = h->rank / px;
+  auto rank_of = [&](int dx, int dy) { return ((by + dy + py) % py) * px + (bx + dx + px) % px; };
+  std::vector<std::pair<int, char *>> mapped;  // rank -> base of its allocation as seen from here
+  std::vector<int> nyl_of(h->world, 0);
+  auto base_of = [&](int r, char **base) -> int {
+    if (r == h->rank) { *base = s.base; nyl_of[r] = s.nyl; return LBM_OK; }
+    for (auto &m : mapped)
+      if (m.first == r) { *base = m.second; return LBM_OK; }
+    const char *b = all + (size_t)r * blob_bytes();
+    cudaIpcMemHandle_t mh;
+    int meta[4];
+    memcpy(&mh, b, sizeof mh);
+    memcpy(meta, b + sizeof mh, sizeof meta);
+    if (meta[0] != r || meta[2] != h->tiles_y || meta[3] != h->ntx)
+      return fail(LBM_E_ARG, "IPC blob %d does not describe rank %d of the same problem", r, r);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(LBM_E_PEER, "cudaIpcOpenMemHandle for rank %d: %s", r, cudaGetErrorString(e));
+    h->ipc_opened.push_back(ptr);
+    mapped.emplace_back(r, static_cast<char *>(ptr));
+    nyl_of[r] = meta[1];
+    *base = static_cast<char *>(ptr);
+    return LBM_OK;
+  };
+  auto lattice = [&](char *base, int b) { return reinterpret_cast<float *>(base + (size_t)b * h->lattice_bytes); };
+  auto flags = [&](char *base) { return reinterpret_cast<int *>(base + 2 * h->lattice_bytes); };
+  char *so = nullptr, *no = nullptr;
+  int rc = base_of(rank_of(0, -1), &so);
+  if (rc == LBM_OK) rc = base_of(rank_of(0, 1), &no);
+  if (rc) return rc;
+  for (int b = 0; b < 2; ++b) {
+    s.south_buf[b] = lattice(so, b);
+    s.north_buf[b] = lattice(no, b);
+  }
+  s.flag_to_south = flags(so) + 1;
+  s.flag_to_north = flags(no) + 0;
+  s.south_ghost_row = nyl_of[rank_of(0, -1)] + 1;
+  const struct { int dx, dy, back; } sides[6] = {{-1, 0, lbm::SIDE_E},  {1, 0, lbm::SIDE_W},   {-1, -1, lbm::SIDE_NE},
+                                                 {1, -1, lbm::SIDE_NW}, {-1, 1, lbm::SIDE_SE}, {1, 1, lbm::SIDE_SW}};
+  for (int i = 0; i < 6; ++i) {
+    char *nb = nullptr;
+    rc = base_of(rank_of(sides[i].dx, sides[i].dy), &nb);
+    if (rc) return rc;
+    for (int b = 0; b < 2; ++b) s.side_buf[i][b] = lattice(nb, b);
+    s.flag_to_side[i] = flags(nb) + 2 + sides[i].back;
+  }
+  h->connected = true;
+  return LBM_OK;
+}
+}  // namespace
+extern "C" {
+
+int lbm_create_rank_grid(lbm_handle **out, int nx, int ny, int max_iters, float density, float accel, float omega, int rank,
+                         int px, int py, int device) {
+  if (!out) return fail(LBM_E_ARG, "null argument");
+  *out = nullptr;
+  if (px < 1 || py < 1 || px > 64 || py > 64) return fail(LBM_E_ARG, "the block grid must be 1..64 x 1..64 (got %d x %d)", px, py);
+  const int world = px * py;
+  if (rank < 0 || rank >= world) return fail(LBM_E_ARG, "bad rank %d of %d", rank, world);
+  int rc = check_problem(nx, ny, max_iters, py);
+  if (rc) return rc;
+  if (nx < px) return fail(LBM_E_ARG, "cannot cut %d columns into %d blocks", nx, px);
+  if ((ny / py + 3 + lbm::kTileH) / lbm::kTileH > 65535)
+    return fail(LBM_E_ARG, "blocks of %d rows exceed the 65535 tile rows of a launch grid: use more block rows", ny / py + 1);
+  int ndev = 0;
+  rc = lbm_device_count(&ndev);
+  if (rc) return rc;
+  if (device < 0 || device >= ndev) return fail(LBM_E_ARG, "GPU %d not visible (%d devices)", device, ndev);
+  lbm_handle *h = new (std::nothrow) lbm_handle();
+  if (!h) return fail(LBM_E_NOMEM, "out of host memory");
+  set_geometry(h, nx, ny, max_iters, density, accel, omega, py, px, true);
+  h->rank_mode = true;
+  h->rank = rank;
+  h->world = world;
+  h->slabs.resize(1);
+  Slab &s = h->slabs[0];
+  s.device = device;
+  lbm::partition::range_of(ny, py, rank / px, s.row0, s.nyl);
+  lbm::partition::range_of(nx, px, rank % px, s.col0, s.nxl);
+  s.ntx_sweep = (s.nxl + lbm::kTileW - 1) / lbm::kTileW;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(LBM_E_CUDA, "stream creation on GPU %d: %s", device, cudaGetErrorString(e));
+  }
+  s.owns_stream = true;
+  rc = create_common(out, h);
+  if (rc) return rc;
+  if (world == 1) return wire_local_grid(h);  // a 1 x 1 "grid" is its own eight neighbours
+  return LBM_OK;
+}
+
 size_t lbm_ipc_blob_bytes(void) { return blob_bytes(); }
 
 int lbm_ipc_export(lbm_handle *h, void *blob) {
@@ -915,6 +1017,7 @@ int lbm_ipc_connect(lbm_handle *h, const void *blobs) {
   if (h->connected) return fail(LBM_E_STATE, "already connected");
   Slab &s = h->slabs[0];
   CUDA_TRY(cudaSetDevice(s.device));
+  if (h->xghost) return connect_block_neighbours(h, static_cast<const char *>(blobs));
   const int w = h->world, south = (h->rank + w - 1) % w, north = (h->rank + 1) % w;
   const char *all = static_cast<const char *>(blobs);
   char *mapped[2] = {nullptr, nullptr};
@@ -966,6 +1069,10 @@ int lbm_ipc_disconnect(lbm_handle *h) {
     Slab &s = h->slabs[0];
     for (int b = 0; b < 2; ++b) s.south_buf[b] = s.north_buf[b] = nullptr;
     s.flag_to_south = s.flag_to_north = nullptr;
+    for (int i = 0; i < 6; ++i) {
+      s.side_buf[i][0] = s.side_buf[i][1] = nullptr;
+      s.flag_to_side[i] = nullptr;
+    }
     h->connected = false;  // compute calls now fail with LBM_E_STATE instead of touching unmapped peer memory
   }
   return LBM_OK;
@@ -995,13 +1102,14 @@ namespace {
 // Global rows [g0, g0 + n) of the problem -> the slabs / blocks that own them.  `cells` / `obstacles` point at row g0 of
 // full-width rows (nx cells apart), from which every block takes its own columns.
 int upload_rows(lbm_handle *h, int g0, int n, const float *cells, const uint8_t *obstacles) {
-  const int nx = h->nx;
+  const int nx = h->rank_block() ? h->slabs[0].nxl : h->nx;  // cells per host row
   for (Slab &s : h->slabs) {
     const int lo = std::max(g0, s.row0), hi = std::min(g0 + n, s.row0 + s.nyl);
     if (lo >= hi) continue;
     CUDA_TRY(cudaSetDevice(s.device));
-    const float *c = cells + ((size_t)(lo - g0) * nx + s.col0) * lbm::kSpeeds;
-    const uint8_t *o = obstacles + (size_t)(lo - g0) * nx + s.col0;
+    const int col = h->rank_block() ? 0 : s.col0;
+    const float *c = cells + ((size_t)(lo - g0) * nx + col) * lbm::kSpeeds;
+    const uint8_t *o = obstacles + (size_t)(lo - g0) * nx + col;
     const int first_storage_row = 1 + (lo - s.row0), nxl = s.nxl;
     // cells: AoS rows -> tiles; obstacles: bytes -> bits.  Chunks of whole rows, PCIe copy of one half of the
     // staging buffer overlapped with the transposition of the other
@@ -1039,14 +1147,15 @@ int drain_all(lbm_handle *h) {
 }
 // Global rows [g0, g0 + n) of the current state -> host AoS / obstacle bytes (either may be null), full-width rows
 int download_rows(lbm_handle *h, int g0, int n, float *cells, uint8_t *obstacles) {
-  const int nx = h->nx;
+  const int nx = h->rank_block() ? h->slabs[0].nxl : h->nx;  // cells per host row
   for (Slab &s : h->slabs) {
     const int lo = std::max(g0, s.row0), hi = std::min(g0 + n, s.row0 + s.nyl);
     if (lo >= hi) continue;
     CUDA_TRY(cudaSetDevice(s.device));
     const int first_storage_row = 1 + (lo - s.row0), nxl = s.nxl;
     if (cells) {
-      int rc = stage_out(s, reinterpret_cast<char *>(cells + ((size_t)(lo - g0) * nx + s.col0) * lbm::kSpeeds),
+      const int col = h->rank_block() ? 0 : s.col0;
+      int rc = stage_out(s, reinterpret_cast<char *>(cells + ((size_t)(lo - g0) * nx + col) * lbm::kSpeeds),
                          (size_t)nx * lbm::kSpeeds * sizeof(float), (size_t)nxl * lbm::kSpeeds * sizeof(float), hi - lo, s.stage_chunk,
                          [&](char *stage, int r, int rows) {
                            lbm::tiles_to_aos_kernel<<<rows * s.ntx_sweep, lbm::kTileW, 0, s.stream>>>(
@@ -1058,7 +1167,8 @@ int download_rows(lbm_handle *h, int g0, int n, float *cells, uint8_t *obstacles
       if (rc) return rc;
     }
     if (obstacles) {
-      int rc = stage_out(s, reinterpret_cast<char *>(obstacles + (size_t)(lo - g0) * nx + s.col0), (size_t)nx, (size_t)nxl, hi - lo,
+      const int col = h->rank_block() ? 0 : s.col0;
+      int rc = stage_out(s, reinterpret_cast<char *>(obstacles + (size_t)(lo - g0) * nx + col), (size_t)nx, (size_t)nxl, hi - lo,
                          s.stage_chunk, [&](char *stage, int r, int rows) {
                            const long long cellsn = (long long)rows * nxl;
                            lbm::unpack_mask_kernel<<<(unsigned)((cellsn + 255) / 256), 256, 0, s.stream>>>(
@@ -1416,12 +1526,12 @@ int lbm_download(lbm_handle *h, float *cells_aos, float *av_vels) {
 int lbm_download_fields(lbm_handle *h, float *fields) {
   if (!h || !fields) return fail(LBM_E_ARG, "null argument");
   if (!h->uploaded) return fail(LBM_E_STATE, "lbm_download_fields before lbm_upload");
-  const int nx = h->nx;
+  const int nx = h->rank_block() ? h->slabs[0].nxl : h->nx;  // cells per host row
   for (Slab &s : h->slabs) {
     CUDA_TRY(cudaSetDevice(s.device));
     const size_t first = h->rank_mode ? 0 : (size_t)s.row0;
-    const int nxl = s.nxl;
-    int rc = stage_out(s, reinterpret_cast<char *>(fields + (first * nx + s.col0) * 4), (size_t)nx * 4 * sizeof(float),
+    const int nxl = s.nxl, col = h->rank_block() ? 0 : s.col0;
+    int rc = stage_out(s, reinterpret_cast<char *>(fields + (first * nx + col) * 4), (size_t)nx * 4 * sizeof(float),
                        (size_t)nxl * 4 * sizeof(float), s.nyl, s.stage_chunk, [&](char *stage, int r, int rows) {
                          lbm::final_state_kernel<<<rows * s.ntx_sweep, lbm::kTileW, 0, s.stream>>>(
                              s.buf[h->cur], s.mask, reinterpret_cast<float4 *>(stage), h->ntx, nxl, rows, 1 + r, h->density, s.ntx_sweep);

@@ -24,6 +24,7 @@ def problem(lbm, nx, ny, iters, seed):
 def main():
     outdir, nx, ny, iters, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     pieces = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+    grid = tuple(int(v) for v in sys.argv[7].split("x")) if len(sys.argv) > 7 else None  # PXxPY: one BLOCK per rank
     import torch
     import torch.distributed as dist
 
@@ -35,11 +36,14 @@ def main():
     slabs = import_module("lbm-graphcore_b200.slabs")
 
     p, cells, obst = problem(lbm, nx, ny, iters, seed)
-    s = lbm.Solver(p, rank=rank, world=world, device=local)
-    slabs.connect_ring(s, dist)
-    r0, n = s.row_begin, s.row_count
-    assert (r0, n) == slabs.slab_rows(rank, world, ny)
-    s.upload(cells[r0:r0 + n], obst[r0:r0 + n])
+    s = lbm.Solver(p, rank=rank, world=world, device=local, grid=grid)
+    slabs.connect_ring(s, dist)  # (all-gather of the IPC blobs + lbm_ipc_connect: the same for slabs and blocks)
+    r0, n, c0, m = s.row_begin, s.row_count, s.col_begin, s.col_count
+    if grid is None:
+        assert (r0, n) == slabs.slab_rows(rank, world, ny) and (c0, m) == (0, nx)
+    else:
+        assert world == grid[0] * grid[1] and s.partition == grid
+    s.upload(cells[r0:r0 + n, c0:c0 + m], obst[r0:r0 + n, c0:c0 + m])
     dist.barrier()  # every rank's lattice is in place before anyone pushes halo rows
     done = 0
     for i in range(pieces):
@@ -49,7 +53,7 @@ def main():
     got, _ = s.download(av_vels=False)
     tot = s.download_tot_u()
     av = slabs.combine_av_vels(dist, tot, s.free_cells)
-    np.savez(os.path.join(outdir, f"rank{rank}.npz"), cells=got, row_begin=r0, tot_u=tot, free_cells=s.free_cells,
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), cells=got, row_begin=r0, col_begin=c0, tot_u=tot, free_cells=s.free_cells,
              av_vels=av, variant=s.kernel_variant)
     slabs.close_ring(s, dist)  # barrier -> unmap the neighbours -> barrier -> free
     dist.destroy_process_group()

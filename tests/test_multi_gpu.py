@@ -104,3 +104,29 @@ def test_block_partition_across_gpus_bit_exact(oracle, lbm, nx, ny, px, py):
         got_cells, got_av = s.download()
     assert np.array_equal(got_cells.view(np.uint32), want_cells.view(np.uint32))
     assert ulp_distance(got_av, want_av).max() <= 1
+
+
+@pytest.mark.parametrize("nx,ny,px,py", [(512, 64, 2, 1), (300, 50, 1, 2), (640, 96, 2, 2), (1024, 128, 4, 2), (777, 90, 2, 4)])
+def test_one_process_per_gpu_block_partition_bit_exact(oracle, lbm, tmp_path, nx, ny, px, py):
+    """torchrun, one rank per GPU, each rank one BLOCK of a px x py partition (lbm_create_rank_grid): up to eight neighbours
+    mapped with CUDA IPC, ghost rows / columns / corners stored into them by the sweep kernel."""
+    world = px * py
+    _need_gpus(lbm, world)
+    iters, seed = 30, 23
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "rank_worker.py"), str(tmp_path), str(nx), str(ny), str(iters), str(seed), "2", f"{px}x{py}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    p, cells, obst = problem(lbm, nx, ny, iters, seed)
+    op = oracle.make_params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    want_cells, want_av = oracle.run(op, cells, obst, iters, accum=oracle.ACCUM_DOUBLE)
+    covered = 0
+    for rank in range(world):
+        z = np.load(tmp_path / f"rank{rank}.npz")
+        r0, c0, got = int(z["row_begin"]), int(z["col_begin"]), z["cells"]
+        want = want_cells[r0:r0 + got.shape[0], c0:c0 + got.shape[1]]
+        assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want).view(np.uint32)), f"rank {rank}"
+        assert ulp_distance(z["av_vels"], want_av).max() <= 1
+        covered += got.shape[0] * got.shape[1]
+    assert covered == nx * ny
