@@ -183,7 +183,9 @@ int lbm_pipeline_solve(lbm_pipeline *p, const float *cells_in, const uint8_t *ob
  * wrap -- (row_count + 2 * margin_rows) rows; the rows outside the window belong to the neighbouring ranks, which exchange
  * them once (host to host) before the job.  In return no rank waits for another during the job: `iters` timesteps of the
  * window depend on nothing else.  cells_out receives the window's row_count rows; tot_u[iters] and *free_cells are this
- * rank's part of the av_vels sums, to be combined in rank order like lbm_download_tot_u's. */
+ * rank's part of the av_vels sums, to be combined in rank order like lbm_download_tot_u's.  A band plus its two margins is
+ * never taller than the grid (it would hold the driven row twice): short grids get shorter bands, and LBM_E_ARG when not even
+ * one 8-row band fits (ny < 8 + 2 * margin_rows). */
 int lbm_pipeline_create_window(lbm_pipeline **out, int nx, int ny, int row_begin, int row_count, int iters, float density,
                                float accel, float omega, int device);
 int lbm_pipeline_solve_window(lbm_pipeline *p, const float *cells_window, const uint8_t *obstacles_window, float *cells_out,

@@ -1816,7 +1816,8 @@ void lbm_pipeline_destroy(lbm_pipeline *p) {
 namespace {
 
 // How a job of `iters` timesteps on `rows` rows (the whole grid, or one rank's window of it) is cut into bands.
-void plan_bands(int nx, int ny, bool window, int rows, int iters, bool &banded, int &band_rows, int &margin) {
+// false: a window that cannot be cut at all (the grid is shorter than one tile row of band plus its two margins)
+bool plan_bands(int nx, int ny, bool window, int rows, int iters, bool &banded, int &band_rows, int &margin) {
   // the margin: >= iters rows, and M + 1 a multiple of the tile height so that a band is whole tile rows of its solver
   margin = ((std::max(iters, 1) + 1 + lbm::kTileH - 1) / lbm::kTileH) * lbm::kTileH - 1;
   const int min_band = (8 * margin + lbm::kTileH - 1) / lbm::kTileH * lbm::kTileH;  // margins at most a quarter of the upload
@@ -1825,8 +1826,15 @@ void plan_bands(int nx, int ny, bool window, int rows, int iters, bool &banded, 
   band_rows = (int)want;
   if (const char *e = getenv("LBM_B200_BAND_ROWS")) band_rows = std::max(lbm::kTileH, atoi(e) / lbm::kTileH * lbm::kTileH);  // tests
   else if (window) band_rows = std::min(rows, std::max(band_rows, min_band));
+  // a band solver drives ONE row: band + margins must not hold the grid's driven row twice, i.e. never be taller than the grid
+  // (whole-grid jobs cannot get there: they band only when ny >= 4 bands and a band >= 8 margins)
+  if (window && band_rows + 2 * margin > ny) {
+    band_rows = (ny - 2 * margin) / lbm::kTileH * lbm::kTileH;
+    if (band_rows < lbm::kTileH) return false;
+  }
   // bands pay when the margins are a small part of a band and there are enough bands to overlap; a window has no other way
   banded = window || (ny % lbm::kTileH == 0 && band_rows >= min_band && ny >= 4 * band_rows && !getenv("LBM_B200_NO_BANDS"));
+  return true;
 }
 
 // window == false: the whole grid (row0 = 0, rows = ny)
@@ -1843,7 +1851,11 @@ int pipeline_create(lbm_pipeline **out, int nx, int ny, bool window, int row0, i
   p->nx = nx; p->ny = ny; p->iters = iters; p->device = device;
   p->density = density; p->accel = accel; p->omega = omega;
   p->window = window; p->row0 = row0; p->rows = rows;
-  plan_bands(nx, ny, window, rows, iters, p->banded, p->band_rows, p->margin);
+  if (!plan_bands(nx, ny, window, rows, iters, p->banded, p->band_rows, p->margin)) {
+    const int m = p->margin;
+    lbm_pipeline_destroy(p);
+    return fail(LBM_E_ARG, "a %d-row grid is too short for a window pipeline of %d timesteps (%d margin rows either side of a band)", ny, iters, m);
+  }
   if (!p->banded) {
     rc = lbm_create_on_devices(&p->whole, nx, ny, iters, density, accel, omega, 1, &device);
     if (rc) { lbm_pipeline_destroy(p); return rc; }
@@ -1989,7 +2001,8 @@ int lbm_pipeline_plan(int nx, int ny, int window_rows, int iters, int *bands, in
   if (window && (rows > ny || rows % lbm::kTileH != 0)) return fail(LBM_E_ARG, "a window must be a multiple of %d rows inside the grid", lbm::kTileH);
   bool banded = false;
   int band = 0, margin = 0;
-  plan_bands(nx, ny, window, rows, iters, banded, band, margin);
+  if (!plan_bands(nx, ny, window, rows, iters, banded, band, margin))
+    return fail(LBM_E_ARG, "a %d-row grid is too short for a window pipeline of %d timesteps (%d margin rows either side of a band)", ny, iters, margin);
   if (bands) *bands = banded ? (rows + band - 1) / band : 1;
   if (band_rows) *band_rows = banded ? band : ny;
   if (margin_rows) *margin_rows = banded ? margin : 0;

@@ -209,6 +209,20 @@ def test_pipeline_plan_without_a_gpu(lbm, monkeypatch):
     assert lbm.pipeline_plan(16384, 16384, 20, window_rows=4096) == {"bands": 4, "band_rows": 1024, "margin_rows": 23}
     assert lbm.pipeline_plan(16384, 16384, 20, window_rows=2048) == {"bands": 4, "band_rows": 512, "margin_rows": 23}
     assert lbm.pipeline_plan(16384, 16384, 100, window_rows=2048) == {"bands": 3, "band_rows": 824, "margin_rows": 103}
-    assert lbm.pipeline_plan(256, 256, 300, window_rows=128)["bands"] == 1  # a window is one band when nothing else fits
+    assert lbm.pipeline_plan(1024, 1024, 300, window_rows=128)["bands"] == 1  # a window is one band when nothing else fits
     with pytest.raises(lbm.LbmError, match="multiple of 8"):
         lbm.pipeline_plan(256, 256, 3, window_rows=100)
+
+
+def test_window_plan_never_holds_the_driven_row_twice(lbm):
+    """A band solver drives one row, so band + 2 x margin must fit in the grid (tests/test_pipeline_model.py shows what happens
+    otherwise): short grids get shorter bands, and a grid with no room for even one tile row of band is refused."""
+    for nx, ny, rows, iters in [(16, 64, 64, 20), (16, 64, 32, 20), (128, 128, 128, 50), (384, 256, 128, 9), (64, 96, 48, 30)]:
+        plan = lbm.pipeline_plan(nx, ny, iters, window_rows=rows)
+        assert plan["margin_rows"] >= iters and (plan["margin_rows"] + 1) % 8 == 0
+        assert plan["band_rows"] % 8 == 0 and plan["band_rows"] >= 8
+        assert plan["band_rows"] + 2 * plan["margin_rows"] <= ny, plan
+        assert plan["bands"] == -(-rows // plan["band_rows"])
+    assert lbm.pipeline_plan(384, 256, 9, window_rows=128) == {"bands": 2, "band_rows": 120, "margin_rows": 15}  # unchanged
+    with pytest.raises(lbm.LbmError, match="too short"):
+        lbm.pipeline_plan(16, 40, 20, window_rows=40)

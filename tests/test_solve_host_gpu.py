@@ -82,7 +82,9 @@ def test_pipeline_is_reusable(oracle, lbm, monkeypatch):
                                                     (256, 512, 4, 5, "32"),
                                                     (384, 256, 2, 9, None),    # margin 15: the two windows see each other's rows twice over
                                                     (128, 192, 3, 3, "64"),    # one band per window
-                                                    (200, 128, 1, 4, "32")])   # a single window that is the whole grid (wraps onto itself)
+                                                    (200, 128, 1, 4, "32"),    # a single window that is the whole grid (wraps onto itself)
+                                                    (64, 64, 1, 20, None),     # margin 23 on a 64-row grid: bands shrink to 16 rows so
+                                                    (128, 96, 2, 25, None)])   # that no band holds the driven row twice (test_pipeline_model.py)
 def test_window_pipelines_reproduce_the_whole_grid(oracle, lbm, monkeypatch, nx, ny, parts, iters, band):
     """lbm_pipeline_create_window: every 'rank' solves its slab from the slab's initial rows plus margin rows of its neighbours,
     independently of the others; together they must give the single-domain oracle's lattice and av_vels."""
@@ -109,5 +111,7 @@ def test_window_argument_errors(lbm):
         lbm.Pipeline(p, 4, window=(0, 100))
     with pytest.raises(lbm.LbmError, match="not inside"):
         lbm.Pipeline(p, 4, window=(200, 128))
+    with pytest.raises(lbm.LbmError, match="too short"):
+        lbm.Pipeline(lbm.Params(64, 40, 20, 10, 0.1, 0.005, 1.85), 20, window=(0, 40))
     with lbm.Pipeline(p, 4, window=(0, 128)) as pipe, pytest.raises(lbm.LbmError, match="window pipeline"):
         pipe.solve_raw(1, 1, 2, None)
