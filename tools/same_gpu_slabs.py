@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Does cutting an L2-resident grid into several row slabs ON THE SAME GPU help?  Each slab is its own launch on its own stream,
-neighbours synchronised by the halo epoch flags instead of stream order, so one slab's tail wave overlaps the next one's head.
+"""Does cutting an L2-resident grid into several row slabs ON THE SAME GPU help?  No: slabs that share a GPU share one stream
+(lbm_create_on_devices), so each step becomes several back-to-back launches without the PDL overlap between timesteps.
 Prints microseconds per timestep for 1 / 2 / 3 / 4 slabs on device 0 and checks the lattices against the 1-slab run (run on a GPU box)."""
 import hashlib
 import importlib
